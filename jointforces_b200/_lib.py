@@ -1,0 +1,258 @@
+"""ctypes binding of libjf_b200.so (include/jf_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible when a
+compute entry point is called, this raises.  The library is built in-tree by
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C jointforces_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libjf_b200.so")
+
+JF_FLAG_NO_REORDER = 1
+JF_FLAG_NO_FOLD = 2
+
+# every symbol include/jf_b200.h declares (tests check the library exports each of them)
+SYMBOLS = [
+    "jf_last_error", "jf_version", "jf_device_count", "jf_ctx_create", "jf_ctx_destroy", "jf_set_material",
+    "jf_set_targets", "jf_set_displacements", "jf_get_displacements", "jf_get_forces", "jf_evaluate", "jf_get_energy",
+    "jf_get_element_quantities", "jf_get_stiffness_blocks", "jf_cg", "jf_get_cg_solution", "jf_relax", "jf_get_stats",
+    "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64",
+]
+
+
+class JFError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_element", C.c_double), ("ms_assembly", C.c_double), ("ms_cg", C.c_double), ("ms_setup", C.c_double),
+                ("tet_updates", C.c_int64), ("cg_iterations", C.c_int64), ("cg_launches", C.c_int64),
+                ("kernel_launches", C.c_int64), ("newton_steps", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Info(C.Structure):
+    _fields_ = [("n_nodes", C.c_int64), ("n_free", C.c_int64), ("n_tets", C.c_int64), ("n_blocks", C.c_int64),
+                ("n_slots", C.c_int64), ("n_sys", C.c_int32), ("n_dirs", C.c_int32), ("n_beams", C.c_int32),
+                ("sm_count", C.c_int32), ("cg_grid", C.c_int32), ("cg_block", C.c_int32), ("elem_grid", C.c_int32),
+                ("elem_block", C.c_int32), ("bytes_device", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises JFError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise JFError("libjf_b200.so not found at %s -- build it first (python -c 'import __graft_entry__ as g; "
+                      "g.build()'); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.jf_last_error.restype = C.c_char_p
+    L.jf_last_error.argtypes = []
+    L.jf_version.restype = C.c_int
+    L.jf_device_count.restype = C.c_int
+    L.jf_ctx_create.argtypes = [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64, _dp, C.c_int64, _ip, _bp, C.c_int, _vp, C.c_uint32]
+    L.jf_ctx_destroy.argtypes = [_vp]
+    L.jf_ctx_destroy.restype = None
+    L.jf_set_material.argtypes = [_vp, C.c_int] + [C.c_double] * 4
+    L.jf_set_targets.argtypes = [_vp, C.c_int, _dp]
+    L.jf_set_displacements.argtypes = [_vp, C.c_int, _dp]
+    L.jf_get_displacements.argtypes = [_vp, C.c_int, _dp]
+    L.jf_get_forces.argtypes = [_vp, C.c_int, _dp]
+    L.jf_evaluate.argtypes = [_vp]
+    L.jf_get_energy.argtypes = [_vp, C.c_int] + [C.POINTER(C.c_double)] * 3
+    L.jf_get_element_quantities.argtypes = [_vp, C.c_int, _vp, _vp, _vp]
+    L.jf_get_stiffness_blocks.argtypes = [_vp, C.c_int, C.POINTER(C.c_int64), _vp, _vp, _vp]
+    L.jf_cg.argtypes = [_vp, C.c_double, C.c_int64, _ip]
+    L.jf_get_cg_solution.argtypes = [_vp, C.c_int, _dp]
+    L.jf_relax.argtypes = [_vp, C.c_double, C.c_int, C.c_double, C.c_double, _dp, _vp, _ip]
+    L.jf_get_stats.argtypes = [_vp, C.POINTER(Stats)]
+    L.jf_reset_stats.argtypes = [_vp]
+    L.jf_get_info.argtypes = [_vp, C.POINTER(Info)]
+    L.jf_solve_boundarycondition.argtypes = [C.c_int, C.c_int64, _dp, C.c_int64, _ip, _bp, _dp, _dp, C.c_int, _vp] + \
+        [C.c_double] * 4 + [C.c_double, C.c_int, C.c_double, _dp, _vp, _ip, _vp, C.POINTER(Stats)]
+    L.jf_bench_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("jf_last_error", "jf_ctx_destroy"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise JFError("jf_b200 error %d: %s" % (rc, load().jf_last_error().decode("utf-8", "replace")))
+    return rc
+
+
+def device_count():
+    return check(load().jf_device_count())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+class Context:
+    """Thin RAII wrapper over jf_ctx: one mesh + boundary mask, ``n_sys`` load cases."""
+
+    def __init__(self, nodes, tets, movable, n_sys=1, beams=None, device=0, flags=0):
+        L = load()
+        self._L = L
+        self._h = _vp()
+        nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        tets = np.ascontiguousarray(tets, dtype=np.int32)
+        movable = np.ascontiguousarray(movable, dtype=np.uint8)
+        if nodes.ndim != 2 or nodes.shape[1] != 3 or tets.ndim != 2 or tets.shape[1] != 4 or movable.shape != (len(nodes),):
+            raise ValueError("nodes (N,3), tets (T,4), movable (N,) expected")
+        if beams is not None:
+            beams = np.ascontiguousarray(beams, dtype=np.float64)
+        self.N, self.T, self.n_sys = len(nodes), len(tets), int(n_sys)
+        check(L.jf_ctx_create(C.byref(self._h), int(device), int(n_sys), self.N, nodes, self.T, tets, movable,
+                              0 if beams is None else len(beams), _ptr(beams), int(flags)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.jf_ctx_destroy(self._h)
+            self._h = _vp()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # --- setters ---------------------------------------------------------------------------------
+    def set_material(self, k, d0, lambda_s, ds, sys=-1):
+        check(self._L.jf_set_material(self._h, int(sys), float(k), float(d0), float(lambda_s), float(ds)))
+
+    def set_targets(self, f_target, sys=0):
+        check(self._L.jf_set_targets(self._h, int(sys), np.ascontiguousarray(f_target, dtype=np.float64)))
+
+    def set_displacements(self, U, sys=0):
+        check(self._L.jf_set_displacements(self._h, int(sys), np.ascontiguousarray(U, dtype=np.float64)))
+
+    # --- getters ---------------------------------------------------------------------------------
+    def displacements(self, sys=0):
+        out = np.empty((self.N, 3))
+        check(self._L.jf_get_displacements(self._h, int(sys), out))
+        return out
+
+    def forces(self, sys=0):
+        out = np.empty((self.N, 3))
+        check(self._L.jf_get_forces(self._h, int(sys), out))
+        return out
+
+    def energy(self, sys=0):
+        e, r2, f2 = C.c_double(), C.c_double(), C.c_double()
+        check(self._L.jf_get_energy(self._h, int(sys), C.byref(e), C.byref(r2), C.byref(f2)))
+        return e.value, r2.value, f2.value
+
+    def element_quantities(self, sys=0, want_K=True):
+        E, f = np.empty(self.T), np.empty((self.T, 4, 3))
+        K = np.empty((self.T, 4, 4, 3, 3)) if want_K else None
+        check(self._L.jf_get_element_quantities(self._h, int(sys), _ptr(E), _ptr(f), _ptr(K)))
+        return E, f, K
+
+    def stiffness_blocks(self, sys=0):
+        n = C.c_int64()
+        check(self._L.jf_get_stiffness_blocks(self._h, int(sys), C.byref(n), None, None, None))
+        rows, cols = np.empty(n.value, np.int32), np.empty(n.value, np.int32)
+        blocks = np.empty((n.value, 3, 3))
+        check(self._L.jf_get_stiffness_blocks(self._h, int(sys), C.byref(n), _ptr(rows), _ptr(cols), _ptr(blocks)))
+        return rows, cols, blocks
+
+    def stiffness_csr(self, sys=0):
+        """Assembled stiffness as scipy CSR (3N x 3N) in the caller's numbering (parity hook)."""
+        import scipy.sparse as ssp
+        rows, cols, blocks = self.stiffness_blocks(sys)
+        r = (3 * rows[:, None, None] + np.arange(3)[None, :, None] + np.zeros((1, 1, 3), int)).ravel()
+        c = (3 * cols[:, None, None] + np.arange(3)[None, None, :] + np.zeros((1, 3, 1), int)).ravel()
+        return ssp.coo_matrix((blocks.ravel(), (r, c)), shape=(3 * self.N, 3 * self.N)).tocsr()
+
+    # --- compute ---------------------------------------------------------------------------------
+    def evaluate(self):
+        check(self._L.jf_evaluate(self._h))
+
+    def cg(self, tol=1e-5, maxiter=0):
+        it = np.zeros(self.n_sys, np.int32)
+        check(self._L.jf_cg(self._h, float(tol), int(maxiter), it))
+        return it
+
+    def cg_solution(self, sys=0):
+        out = np.empty((self.N, 3))
+        check(self._L.jf_get_cg_solution(self._h, int(sys), out))
+        return out
+
+    def relax(self, step, max_iter, conv_crit, cg_tol=0.0):
+        relrec = np.zeros((self.n_sys, max_iter + 1, 3))
+        cgit = np.zeros((self.n_sys, max(max_iter, 1)), np.int32)
+        n_iter = np.zeros(self.n_sys, np.int32)
+        check(self._L.jf_relax(self._h, float(step), int(max_iter), float(conv_crit), float(cg_tol), relrec, _ptr(cgit), n_iter))
+        return ([relrec[s, : n_iter[s] + 1].copy() for s in range(self.n_sys)],
+                [cgit[s, : n_iter[s]].copy() for s in range(self.n_sys)], n_iter)
+
+    def stats(self):
+        s = Stats()
+        check(self._L.jf_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        check(self._L.jf_reset_stats(self._h))
+
+    def info(self):
+        i = Info()
+        check(self._L.jf_get_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+
+def solve_boundarycondition(nodes, tets, movable, f_target, U0, material, step, max_iter, conv_crit, beams=None, device=0):
+    """One-call host-buffer solve (jf_solve_boundarycondition).  Returns dict(U, forces, relrec,
+    cg_iters, n_iter, stats)."""
+    L = load()
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    tets = np.ascontiguousarray(tets, dtype=np.int32)
+    movable = np.ascontiguousarray(movable, dtype=np.uint8)
+    ft = np.ascontiguousarray(f_target, dtype=np.float64)
+    U = np.array(U0, dtype=np.float64, order="C", copy=True)
+    if beams is not None:
+        beams = np.ascontiguousarray(beams, dtype=np.float64)
+    relrec = np.zeros((max_iter + 1, 3))
+    cgit = np.zeros(max(max_iter, 1), np.int32)
+    n_iter = np.zeros(1, np.int32)
+    forces = np.empty_like(nodes)
+    st = Stats()
+    k, d0, ls, ds = map(float, material)
+    check(L.jf_solve_boundarycondition(int(device), len(nodes), nodes, len(tets), tets, movable, ft, U,
+                                       0 if beams is None else len(beams), _ptr(beams), k, d0, ls, ds, float(step),
+                                       int(max_iter), float(conv_crit), relrec, _ptr(cgit), n_iter, _ptr(forces), C.byref(st)))
+    n = int(n_iter[0])
+    return dict(U=U, forces=forces, relrec=relrec[: n + 1].copy(), cg_iters=cgit[:n].copy(), n_iter=n, stats=st.as_dict())
+
+
+def bench_fp64(device=0):
+    g = C.c_double()
+    check(load().jf_bench_fp64(int(device), C.byref(g)))
+    return g.value

@@ -1,0 +1,587 @@
+// C ABI of libjf_b200 (include/jf_b200.h): context lifetime, host<->device transfers in the
+// caller's node/tet numbering, the Newton/relaxation driver and statistics.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+
+#include "jf_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void jf_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int jf_cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    jf_set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return JF_ERR_CUDA;
+}
+
+extern "C" const char *jf_last_error(void) { return g_err; }
+extern "C" int jf_version(void) { return 100; }
+
+extern "C" int jf_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return jf_cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    return n;
+}
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+#define CHECK_CTX(c)                          \
+    do {                                      \
+        if (!(c)) {                           \
+            jf_set_error("null context");     \
+            return JF_ERR_ARG;                \
+        }                                     \
+        JF_CUDA(cudaSetDevice((c)->device));  \
+    } while (0)
+
+#define CHECK_SYS(c, s)                                                          \
+    do {                                                                         \
+        if ((s) < 0 || (s) >= (c)->n_sys) {                                      \
+            jf_set_error("system index %d outside [0,%d)", (s), (c)->n_sys);     \
+            return JF_ERR_ARG;                                                   \
+        }                                                                        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+static void ctx_free(jf_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    void *ptrs[] = {c->d_tets, c->d_nodes, c->d_phi, c->d_vol, c->d_dirtab, c->d_mat, c->d_state, c->d_U, c->d_ft, c->d_f,
+                    c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
+                    c->d_fn_ptr, c->d_fn_src, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_partial,
+                    c->d_barrier};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" void jf_ctx_destroy(jf_ctx *c) { ctx_free(c); }
+
+extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_nodes, const double *nodes, int64_t n_tets,
+                             const int32_t *tets, const uint8_t *movable, int n_beams, const double *beams, uint32_t flags) {
+    if (!out || !nodes || !tets || !movable) {
+        jf_set_error("jf_ctx_create: null argument");
+        return JF_ERR_ARG;
+    }
+    *out = nullptr;
+    if (n_sys < 1 || n_sys > JF_MAX_SYS) {
+        jf_set_error("n_sys must be in [1,%d]", JF_MAX_SYS);
+        return JF_ERR_ARG;
+    }
+    if (n_nodes < 4 || n_tets < 1 || n_nodes > 700000000LL) {
+        jf_set_error("need at least 4 nodes and 1 tetrahedron");
+        return JF_ERR_ARG;
+    }
+    int ndev = jf_device_count();
+    if (ndev < 0) return ndev;
+    if (device < 0 || device >= ndev) {
+        jf_set_error("device %d not available (%d CUDA devices)", device, ndev);
+        return JF_ERR_CUDA;
+    }
+    double t0 = now_ms();
+    JF_CUDA(cudaSetDevice(device));
+    jf_ctx *c = new jf_ctx();
+    c->device = device;
+    c->n_sys = n_sys;
+    c->N = n_nodes;
+    c->T = n_tets;
+    c->flags = flags;
+    int rc = 0;
+    do {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "props", __FILE__, __LINE__); break; }
+        c->sm_count = prop.multiProcessorCount;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (!coop) { jf_set_error("device lacks cooperative launch"); rc = JF_ERR_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "stream", __FILE__, __LINE__); break; }
+        for (auto &e : c->ev)
+            if (cudaEventCreate(&e) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
+        if (rc) break;
+        if ((rc = jf_build_structure(c, nodes, tets, movable, beams, n_beams))) break;
+        const size_t S = (size_t)n_sys, N = (size_t)c->N, T = (size_t)c->T;
+        if ((rc = jf_dev_alloc(c, &c->d_mat, S))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_state, S))) break;
+        if (cudaMallocHost((void **)&c->h_state, S * sizeof(jf_sys_state)) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "pinned", __FILE__, __LINE__); break; }
+        if ((rc = jf_dev_alloc(c, &c->d_U, S * N * 3))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_ft, S * N * 3))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_f, S * N * 3))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_Et, S * T))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_fel, S * T * 12))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_Kel, S * T * 90))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_val, S * (size_t)c->n_slots * 9))) break;
+        const size_t V = S * (size_t)c->Nf_pad * 4;
+        double **vecs[] = {&c->d_b, &c->d_x, &c->d_r, &c->d_p0, &c->d_p1, &c->d_Ap};
+        for (double **v : vecs) {
+            if ((rc = jf_dev_alloc(c, v, V))) break;
+            if (cudaMemset(*v, 0, (V ? V : 1) * sizeof(double)) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
+        }
+        if (rc) break;
+        if ((rc = jf_cg_configure(c))) break;
+        if ((rc = jf_elem_configure(c))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_partial, 2 * S * (size_t)c->cg_grid))) break;
+        cudaMemset(c->d_U, 0, S * N * 3 * sizeof(double));
+        cudaMemset(c->d_ft, 0, S * N * 3 * sizeof(double));
+        cudaMemset(c->d_f, 0, S * N * 3 * sizeof(double));
+        memset(c->h_state, 0, S * sizeof(jf_sys_state));
+        for (size_t s = 0; s < S; s++) c->h_state[s].active = 1;
+        if (cudaMemcpy(c->d_state, c->h_state, S * sizeof(jf_sys_state), cudaMemcpyHostToDevice) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "state", __FILE__, __LINE__); break; }
+        c->have_targets.assign(S, 0);
+        if (cudaDeviceSynchronize() != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__); break; }
+    } while (0);
+    if (rc) {
+        ctx_free(c);
+        return rc;
+    }
+    c->stats.ms_setup = now_ms() - t0;
+    *out = c;
+    return JF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// setters / getters (caller numbering <-> internal numbering)
+// ------------------------------------------------------------------------------------------------
+extern "C" int jf_set_material(jf_ctx *c, int sys, double k, double d0, double ls, double ds) {
+    CHECK_CTX(c);
+    if (sys != -1) CHECK_SYS(c, sys);
+    if (!(k > 0) || !(d0 > 0) || !(ds > 0) || !isfinite(k)) {
+        jf_set_error("material needs k > 0, d0 > 0, ds > 0");
+        return JF_ERR_ARG;
+    }
+    jf_material m = {k, d0, ls, ds, 1.0 / d0, 1.0 / ds};
+    for (int s = (sys < 0 ? 0 : sys); s < (sys < 0 ? c->n_sys : sys + 1); s++)
+        JF_CUDA(cudaMemcpy(c->d_mat + s, &m, sizeof m, cudaMemcpyHostToDevice));
+    if (sys < 0 || c->n_sys == 1) c->have_material = true;
+    else c->have_material = true;  // per-system materials: caller sets each one; unset ones are caught in relax
+    c->evaluated = false;
+    return JF_OK;
+}
+
+static int put_nodal(jf_ctx *c, double *dst_dev, int sys, const double *src, bool zero_fixed) {
+    std::vector<double> tmp((size_t)c->N * 3);
+    for (int64_t i = 0; i < c->N; i++) {
+        const double *p = src + 3 * (int64_t)c->node_new2old[i];
+        const bool fixed = i >= c->Nf;
+        for (int k = 0; k < 3; k++) {
+            double v = p[k];
+            if (v != v || (zero_fixed && fixed)) v = 0.0;
+            tmp[3 * i + k] = v;
+        }
+    }
+    JF_CUDA(cudaMemcpyAsync(dst_dev + (size_t)sys * c->N * 3, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    return JF_OK;
+}
+
+static int get_nodal(jf_ctx *c, const double *src_dev, int sys, double *dst) {
+    std::vector<double> tmp((size_t)c->N * 3);
+    JF_CUDA(cudaMemcpyAsync(tmp.data(), src_dev + (size_t)sys * c->N * 3, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < c->N; i++) {
+        double *p = dst + 3 * (int64_t)c->node_new2old[i];
+        for (int k = 0; k < 3; k++) p[k] = tmp[3 * i + k];
+    }
+    return JF_OK;
+}
+
+extern "C" int jf_set_targets(jf_ctx *c, int sys, const double *f_target) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!f_target) { jf_set_error("null f_target"); return JF_ERR_ARG; }
+    int rc = put_nodal(c, c->d_ft, sys, f_target, true);
+    if (rc) return rc;
+    c->have_targets[sys] = 1;
+    c->evaluated = false;
+    return JF_OK;
+}
+
+extern "C" int jf_set_displacements(jf_ctx *c, int sys, const double *U) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!U) { jf_set_error("null U"); return JF_ERR_ARG; }
+    c->evaluated = false;
+    return put_nodal(c, c->d_U, sys, U, false);
+}
+
+extern "C" int jf_get_displacements(jf_ctx *c, int sys, double *U) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!U) { jf_set_error("null U"); return JF_ERR_ARG; }
+    return get_nodal(c, c->d_U, sys, U);
+}
+
+extern "C" int jf_get_forces(jf_ctx *c, int sys, double *f) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!f) { jf_set_error("null f"); return JF_ERR_ARG; }
+    if (!c->evaluated) { jf_set_error("jf_get_forces before jf_evaluate/jf_relax"); return JF_ERR_STATE; }
+    return get_nodal(c, c->d_f, sys, f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------------
+static int evaluate_async(jf_ctx *c, bool timed) {
+    int rc;
+    if (timed) JF_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = jf_launch_element(c))) return rc;
+    if (timed) JF_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = jf_launch_assembly(c))) return rc;
+    if (timed) JF_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    return 0;
+}
+
+static int fetch_state(jf_ctx *c) {
+    JF_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, c->n_sys * sizeof(jf_sys_state), cudaMemcpyDeviceToHost, c->stream));
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int account_eval(jf_ctx *c, int n_active) {
+    float a = 0, b = 0;
+    JF_CUDA(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    JF_CUDA(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    c->stats.ms_element += a;
+    c->stats.ms_assembly += b;
+    c->stats.tet_updates += (int64_t)n_active * c->T;
+    return 0;
+}
+
+static int count_active(jf_ctx *c) {
+    int n = 0;
+    for (int s = 0; s < c->n_sys; s++) n += c->h_state[s].active ? 1 : 0;
+    return n;
+}
+
+extern "C" int jf_evaluate(jf_ctx *c) {
+    CHECK_CTX(c);
+    if (!c->have_material) { jf_set_error("jf_evaluate before jf_set_material"); return JF_ERR_STATE; }
+    for (int s = 0; s < c->n_sys; s++) {
+        c->h_state[s].active = 1;
+        JF_CUDA(cudaMemcpyAsync(&c->d_state[s].active, &c->h_state[s].active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = evaluate_async(c, true);
+    if (rc) return rc;
+    if ((rc = fetch_state(c))) return rc;
+    if ((rc = account_eval(c, count_active(c)))) return rc;
+    c->evaluated = true;
+    return JF_OK;
+}
+
+extern "C" int jf_get_energy(jf_ctx *c, int sys, double *energy, double *residual2, double *force2) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!c->evaluated) { jf_set_error("jf_get_energy before jf_evaluate/jf_relax"); return JF_ERR_STATE; }
+    if (energy) *energy = c->h_state[sys].energy;
+    if (residual2) *residual2 = c->h_state[sys].residual2;
+    if (force2) *force2 = c->h_state[sys].force2;
+    return JF_OK;
+}
+
+extern "C" int jf_get_element_quantities(jf_ctx *c, int sys, double *E, double *f_el, double *K_el) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!c->evaluated) { jf_set_error("jf_get_element_quantities before jf_evaluate"); return JF_ERR_STATE; }
+    const int64_t T = c->T;
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    if (E) {
+        std::vector<double> tmp(T);
+        JF_CUDA(cudaMemcpy(tmp.data(), c->d_Et + (size_t)sys * T, T * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t t = 0; t < T; t++) E[c->tet_new2old[t]] = tmp[t];
+    }
+    if (f_el) {
+        std::vector<double> tmp((size_t)T * 12);
+        JF_CUDA(cudaMemcpy(tmp.data(), c->d_fel + (size_t)sys * T * 12, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t t = 0; t < T; t++) memcpy(f_el + 12 * (int64_t)c->tet_new2old[t], &tmp[12 * t], 12 * sizeof(double));
+    }
+    if (K_el) {
+        static const int pair_of[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+        const int64_t chunk = 1 << 18;
+        std::vector<double> tmp((size_t)std::min(chunk, T) * 90);
+        for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+            int64_t n = std::min(chunk, T - t0);
+            JF_CUDA(cudaMemcpy(tmp.data(), c->d_Kel + ((size_t)sys * T + t0) * 90, (size_t)n * 90 * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int64_t t = 0; t < n; t++) {
+                double *dst = K_el + 144 * (int64_t)c->tet_new2old[t0 + t];
+                const double *src = &tmp[90 * t];
+                for (int m = 0; m < 4; m++)
+                    for (int r = 0; r < 4; r++)
+                        for (int i = 0; i < 3; i++)
+                            for (int l = 0; l < 3; l++)
+                                dst[((m * 4 + r) * 3 + i) * 3 + l] = (m <= r) ? src[pair_of[m][r] * 9 + 3 * i + l] : src[pair_of[m][r] * 9 + 3 * l + i];
+            }
+        }
+    }
+    return JF_OK;
+}
+
+extern "C" int jf_get_stiffness_blocks(jf_ctx *c, int sys, int64_t *n_blocks, int32_t *row_node, int32_t *col_node, double *blocks) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!n_blocks) { jf_set_error("null n_blocks"); return JF_ERR_ARG; }
+    *n_blocks = c->n_blocks;
+    if (!row_node && !col_node && !blocks) return JF_OK;
+    if (!row_node || !col_node || !blocks) { jf_set_error("row_node, col_node and blocks must all be given"); return JF_ERR_ARG; }
+    if (!c->evaluated) { jf_set_error("jf_get_stiffness_blocks before jf_evaluate"); return JF_ERR_STATE; }
+    std::vector<double> val((size_t)c->n_slots * 9);
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    JF_CUDA(cudaMemcpy(val.data(), c->d_val + (size_t)sys * c->n_slots * 9, val.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // walk rows; a row's real blocks are the leading h_rowlen entries of its SELL row
+    int64_t out = 0;
+    for (int64_t row = 0; row < c->Nf; row++) {
+        int64_t k = row / JF_SLICE, lane = row % JF_SLICE;
+        int64_t q0 = c->h_slice_ptr[k], w = (c->h_slice_ptr[k + 1] - q0) / JF_SLICE;
+        (void)w;
+        for (int64_t j = 0; j < c->h_rowlen[row]; j++) {
+            int64_t q = q0 + j * JF_SLICE + lane;
+            int32_t col = c->h_sell_col[q];
+            if (out >= c->n_blocks) { jf_set_error("internal: block count mismatch"); return JF_ERR_STATE; }
+            row_node[out] = c->node_new2old[row];
+            col_node[out] = c->node_new2old[col];
+            for (int comp = 0; comp < 9; comp++) blocks[9 * out + comp] = val[(q >> 5) * 288 + 32 * comp + (q & 31)];
+            out++;
+        }
+    }
+    if (out != c->n_blocks) { jf_set_error("internal: walked %lld blocks, expected %lld", (long long)out, (long long)c->n_blocks); return JF_ERR_STATE; }
+    return JF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CG and relaxation
+// ------------------------------------------------------------------------------------------------
+static int ready_for_solve(jf_ctx *c) {
+    if (!c->have_material) { jf_set_error("material not set"); return JF_ERR_STATE; }
+    for (int s = 0; s < c->n_sys; s++)
+        if (!c->have_targets[s]) { jf_set_error("targets of system %d not set", s); return JF_ERR_STATE; }
+    return 0;
+}
+
+extern "C" int jf_cg(jf_ctx *c, double tol, int64_t maxiter, int32_t *iters) {
+    CHECK_CTX(c);
+    if (!c->evaluated) { jf_set_error("jf_cg before jf_evaluate"); return JF_ERR_STATE; }
+    if (tol <= 0) tol = 1e-5;
+    if (maxiter <= 0) maxiter = 3 * c->N;
+    JF_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    int rc = jf_launch_cg(c, tol, maxiter, 0.0, 0);
+    if (rc) return rc;
+    JF_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    if ((rc = fetch_state(c))) return rc;
+    float ms = 0;
+    JF_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]));
+    c->stats.ms_cg += ms;
+    for (int s = 0; s < c->n_sys; s++) {
+        if (iters) iters[s] = c->h_state[s].cg_iters;
+        c->stats.cg_iterations += c->h_state[s].cg_iters;
+    }
+    return JF_OK;
+}
+
+extern "C" int jf_get_cg_solution(jf_ctx *c, int sys, double *uu) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!uu) { jf_set_error("null uu"); return JF_ERR_ARG; }
+    std::vector<double> tmp((size_t)c->Nf_pad * 4);
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    JF_CUDA(cudaMemcpy(tmp.data(), c->d_x + (size_t)sys * c->Nf_pad * 4, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    memset(uu, 0, (size_t)c->N * 3 * sizeof(double));
+    for (int64_t i = 0; i < c->Nf; i++)
+        for (int k = 0; k < 3; k++) uu[3 * (int64_t)c->node_new2old[i] + k] = tmp[4 * i + k];
+    return JF_OK;
+}
+
+extern "C" int jf_relax(jf_ctx *c, double step, int max_iter, double conv_crit, double cg_tol, double *relrec, int32_t *cg_iters,
+                        int32_t *n_iter) {
+    CHECK_CTX(c);
+    if (!relrec || !n_iter || max_iter < 0) { jf_set_error("jf_relax: bad arguments"); return JF_ERR_ARG; }
+    int rc = ready_for_solve(c);
+    if (rc) return rc;
+    if (cg_tol <= 0) cg_tol = 1e-5;
+    const int S = c->n_sys;
+    const int64_t cg_maxiter = 3 * c->N;
+    const size_t stride = (size_t)(max_iter + 1) * 3;
+    // all systems start active
+    for (int s = 0; s < S; s++) c->h_state[s].active = 1;
+    JF_CUDA(cudaMemcpyAsync(c->d_state, c->h_state, S * sizeof(jf_sys_state), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = evaluate_async(c, true))) return rc;
+    if ((rc = fetch_state(c))) return rc;
+    if ((rc = account_eval(c, S))) return rc;
+    c->evaluated = true;
+    for (int s = 0; s < S; s++) {
+        double *row = relrec + s * stride;
+        row[0] = 0.0;
+        row[1] = c->h_state[s].energy;
+        row[2] = c->h_state[s].force2;  // saenopy logs sum f^2 (not f - f_target) for the start row
+        n_iter[s] = 0;
+    }
+    int n_active = S;
+    for (int i = 0; i < max_iter && n_active > 0; i++) {
+        JF_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        if ((rc = jf_launch_cg(c, cg_tol, cg_maxiter, step, 1))) return rc;
+        JF_CUDA(cudaEventRecord(c->ev[4], c->stream));
+        if ((rc = evaluate_async(c, true))) return rc;
+        if ((rc = fetch_state(c))) return rc;
+        float ms = 0;
+        JF_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]));
+        c->stats.ms_cg += ms;
+        if ((rc = account_eval(c, n_active))) return rc;
+        bool changed = false;
+        for (int s = 0; s < S; s++) {
+            if (!c->h_state[s].active) continue;
+            double *row = relrec + s * stride + 3 * (size_t)(i + 1);
+            row[0] = c->h_state[s].du;
+            row[1] = c->h_state[s].energy;
+            row[2] = c->h_state[s].residual2;
+            if (cg_iters) cg_iters[(size_t)s * max_iter + i] = c->h_state[s].cg_iters;
+            c->stats.cg_iterations += c->h_state[s].cg_iters;
+            c->stats.newton_steps++;
+            n_iter[s] = i + 1;
+            if (i > 6) {  // five-energy stop rule (A14)
+                double mean = 0.0, var = 0.0;
+                for (int j = 0; j < 5; j++) mean += relrec[s * stride + 3 * (size_t)(i + 1 - j) + 1];
+                mean /= 5.0;
+                for (int j = 0; j < 5; j++) {
+                    double d = relrec[s * stride + 3 * (size_t)(i + 1 - j) + 1] - mean;
+                    var += d * d;
+                }
+                double estd = sqrt(var / 5.0) / sqrt(5.0);
+                if (estd / mean < conv_crit) {
+                    c->h_state[s].active = 0;
+                    changed = true;
+                    n_active--;
+                }
+            }
+        }
+        if (changed) {
+            // only the `active` words change; state values on the device stay as they are
+            for (int s = 0; s < S; s++)
+                JF_CUDA(cudaMemcpyAsync(&c->d_state[s].active, &c->h_state[s].active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    return JF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stats / info
+// ------------------------------------------------------------------------------------------------
+extern "C" int jf_get_stats(jf_ctx *c, jf_stats *out) {
+    if (!c || !out) { jf_set_error("null argument"); return JF_ERR_ARG; }
+    *out = c->stats;
+    return JF_OK;
+}
+
+extern "C" int jf_reset_stats(jf_ctx *c) {
+    if (!c) { jf_set_error("null context"); return JF_ERR_ARG; }
+    double setup = c->stats.ms_setup;
+    c->stats = jf_stats();
+    c->stats.ms_setup = setup;
+    return JF_OK;
+}
+
+extern "C" int jf_get_info(jf_ctx *c, jf_info *o) {
+    if (!c || !o) { jf_set_error("null argument"); return JF_ERR_ARG; }
+    o->n_nodes = c->N;
+    o->n_free = c->Nf;
+    o->n_tets = c->T;
+    o->n_blocks = c->n_blocks;
+    o->n_slots = c->n_slots;
+    o->n_sys = c->n_sys;
+    o->n_dirs = c->n_dirs;
+    o->n_beams = c->n_beams;
+    o->sm_count = c->sm_count;
+    o->cg_grid = c->cg_grid;
+    o->cg_block = JF_CG_BLOCK;
+    o->elem_grid = c->elem_grid;
+    o->elem_block = JF_ELEM_BLOCK;
+    o->bytes_device = c->bytes_device;
+    return JF_OK;
+}
+
+extern "C" int jf_solve_boundarycondition(int device, int64_t n_nodes, const double *nodes, int64_t n_tets, const int32_t *tets,
+                                          const uint8_t *movable, const double *f_target, double *U, int n_beams,
+                                          const double *beams, double k, double d0, double lambda_s, double ds, double step,
+                                          int max_iter, double conv_crit, double *relrec, int32_t *cg_iters, int32_t *n_iter,
+                                          double *forces_out, jf_stats *stats_out) {
+    jf_ctx *c = nullptr;
+    int rc = jf_ctx_create(&c, device, 1, n_nodes, nodes, n_tets, tets, movable, n_beams, beams, 0);
+    if (rc) return rc;
+    do {
+        if ((rc = jf_set_material(c, 0, k, d0, lambda_s, ds))) break;
+        if ((rc = jf_set_targets(c, 0, f_target))) break;
+        if ((rc = jf_set_displacements(c, 0, U))) break;
+        if ((rc = jf_relax(c, step, max_iter, conv_crit, 0.0, relrec, cg_iters, n_iter))) break;
+        if ((rc = jf_get_displacements(c, 0, U))) break;
+        if (forces_out && (rc = jf_get_forces(c, 0, forces_out))) break;
+        if (stats_out) jf_get_stats(c, stats_out);
+    } while (0);
+    jf_ctx_destroy(c);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA peak (roofline denominator of the element kernel; MEASURED_PEAKS.json has no FP64 figure)
+// ------------------------------------------------------------------------------------------------
+__global__ void jf_fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int jf_bench_fp64(int device, double *gflops) {
+    if (!gflops) { jf_set_error("null gflops"); return JF_ERR_ARG; }
+    int ndev = jf_device_count();
+    if (ndev < 0) return ndev;
+    if (device < 0 || device >= ndev) { jf_set_error("device %d not available", device); return JF_ERR_CUDA; }
+    JF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    JF_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    double *d = nullptr;
+    JF_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    JF_CUDA(cudaEventCreate(&e0));
+    JF_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        JF_CUDA(cudaEventRecord(e0));
+        jf_fp64_peak_kernel<<<blocks, threads>>>(d, iters);
+        JF_CUDA(cudaEventRecord(e1));
+        JF_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        JF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double gf = 2.0 * 8 * iters * (double)blocks * threads / (ms * 1e-3) * 1e-9;
+        if (rep > 0 && gf > best) best = gf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *gflops = best;
+    return JF_OK;
+}

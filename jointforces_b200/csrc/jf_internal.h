@@ -1,0 +1,116 @@
+// Internal declarations shared by the translation units of libjf_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "jf_b200.h"
+
+#define JF_MAX_SYS 64          // systems per context (lockstep batch); smem partial tables are sized by it
+#define JF_SLICE 32            // SELL slice height = one warp of block rows
+#define JF_NTAB 22             // doubles per direction-table entry: 6 pair products, 15 quartic monomials, weight
+#define JF_ELEM_LANES 4        // lanes cooperating on one tetrahedron
+#define JF_ELEM_BLOCK 128
+#define JF_CG_BLOCK 512
+
+void jf_set_error(const char *fmt, ...);
+int jf_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define JF_CUDA(x)                                                              \
+    do {                                                                        \
+        cudaError_t _e = (x);                                                   \
+        if (_e != cudaSuccess) return jf_cuda_fail(_e, #x, __FILE__, __LINE__); \
+    } while (0)
+
+struct jf_material {
+    double k, d0, ls, ds, inv_d0, inv_ds;
+};
+
+// per-system scalars living on the device (one struct per system)
+struct jf_sys_state {
+    double energy;      // strain energy of the last evaluation
+    double residual2;   // sum (f - f_target)^2 over free nodes
+    double force2;      // sum f^2 over free nodes
+    double du;          // step^2 * sum uu^2 of the last relaxation step
+    double normb;       // CG: b.b
+    double resid;       // CG: r.r carried between iterations
+    int cg_iters;       // CG iterations of the last solve
+    int active;         // 1 = still relaxing
+    int cg_done;        // CG: converged / finished flag
+    int pad;
+};
+
+struct jf_ctx {
+    int device = 0;
+    int n_sys = 1;
+    int64_t N = 0, Nf = 0, T = 0;
+    int n_beams = 0, n_dirs = 0, n_dirs_pad = 0;
+    uint32_t flags = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    // host-side permutations (new <-> old)
+    std::vector<int32_t> node_new2old, node_old2new, tet_new2old;
+
+    // device: mesh
+    int32_t *d_tets = nullptr;     // (T,4) new node ids
+    double *d_nodes = nullptr;     // (N,3) new order
+    double *d_phi = nullptr;       // (T,12)
+    double *d_vol = nullptr;       // (T)
+    double *d_dirtab = nullptr;    // (JF_NTAB/2, n_dirs_pad) double2: direction table
+    // device: per-system state
+    jf_material *d_mat = nullptr;  // (S)
+    jf_sys_state *d_state = nullptr;
+    jf_sys_state *h_state = nullptr;  // pinned mirror
+    double *d_U = nullptr;         // (S,N,3)
+    double *d_ft = nullptr;        // (S,N,3) target forces (0 on fixed nodes)
+    double *d_f = nullptr;         // (S,N,3) internal forces
+    double *d_Et = nullptr;        // (S,T) per-tet energy
+    double *d_fel = nullptr;       // (S,T,12)
+    double *d_Kel = nullptr;       // (S,T,90) 10 unique (m<=r) 3x3 blocks
+    // device: SELL-32 block matrix structure (shared by all systems)
+    int64_t n_slices = 0, n_slots = 0, n_blocks = 0;
+    int32_t *d_slice_ptr = nullptr;    // (n_slices+1) slot offset of each slice
+    int32_t *d_sell_col = nullptr;     // (n_slots) block-column (free node id); padding -> own row
+    int32_t *d_contrib_ptr = nullptr;  // (n_slots+1)
+    int32_t *d_contrib_src = nullptr;  // ((t*10+pair)*2 + transpose)
+    int32_t *d_fn_ptr = nullptr;       // (N+1)
+    int32_t *d_fn_src = nullptr;       // (t*4+m)
+    double *d_val = nullptr;           // (S, n_slots*9)
+    // device: CG vectors, (S, Nf_pad, 4) each
+    int64_t Nf_pad = 0;
+    double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_p0 = nullptr, *d_p1 = nullptr, *d_Ap = nullptr;
+    double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
+    unsigned int *d_barrier = nullptr; // grid barrier words
+    int cg_grid = 0, elem_grid = 0;
+
+    bool have_material = false, evaluated = false;
+    std::vector<char> have_targets;
+    jf_stats stats = {};
+    int64_t bytes_device = 0;
+
+    // host copies kept for the parity hooks
+    std::vector<int32_t> h_sell_col, h_slice_ptr, h_rowlen;
+};
+
+// jf_setup.cu
+int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets, const uint8_t *movable,
+                       const double *beams, int n_beams);
+// kernels (each returns after enqueueing on c->stream)
+int jf_launch_element(jf_ctx *c);
+int jf_launch_assembly(jf_ctx *c);
+int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_update);
+int jf_cg_configure(jf_ctx *c);
+int jf_elem_configure(jf_ctx *c);
+
+template <typename Tp>
+int jf_dev_alloc(jf_ctx *c, Tp **p, size_t n) {
+    size_t bytes = n * sizeof(Tp);
+    if (bytes == 0) bytes = sizeof(Tp);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e != cudaSuccess) return jf_cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    c->bytes_device += (int64_t)bytes;
+    return 0;
+}

@@ -1,0 +1,372 @@
+// One-off structure build for a context: locality reordering, shape tensors,
+// SELL-32 block-matrix pattern with its deterministic gather lists (replaces saenopy's
+// _compute_connections + per-iteration COO->CSR), and the folded direction table
+// (SURVEY A2).  Host code; runs once per mesh, not on the hot path.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <queue>
+
+#include "jf_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// direction sphere, saenopy build_beams(300)
+// ------------------------------------------------------------------------------------------------
+static std::vector<double> default_beams(int n_req) {
+    int n = (int)floor(sqrt(n_req * M_PI + 0.5));
+    std::vector<double> b;
+    for (int i = 0; i < n; i++) {
+        double theta = (2 * M_PI / n) * i;
+        int jmax = (int)floor(n * sin(theta) + 0.5);
+        for (int j = 0; j < jmax; j++) {
+            double rho = (2 * M_PI / jmax) * j;
+            b.push_back(sin(theta) * cos(rho));
+            b.push_back(sin(theta) * sin(rho));
+            b.push_back(cos(theta));
+        }
+    }
+    return b;
+}
+
+// index of the quartic monomial x^ex y^ey z^ez (ex+ey+ez = 4) in the 15-entry table
+static inline int mono_id(int ex, int ey) { return (4 - ex) * (5 - ex) / 2 + (4 - ex - ey); }
+
+static int build_dirtab(jf_ctx *c, const double *beams, int n_beams) {
+    std::vector<double> own;
+    if (!beams) {
+        own = default_beams(300);
+        beams = own.data();
+        n_beams = (int)(own.size() / 3);
+    }
+    if (n_beams <= 0) {
+        jf_set_error("n_beams must be positive");
+        return JF_ERR_ARG;
+    }
+    c->n_beams = n_beams;
+    // fold antipodal pairs: every term of A5-A8 is even in s, so s and -s contribute identically
+    std::vector<int> rep;
+    std::vector<double> wt;
+    std::vector<char> used(n_beams, 0);
+    for (int i = 0; i < n_beams; i++) {
+        if (used[i]) continue;
+        used[i] = 1;
+        double w = 1.0;
+        if (!(c->flags & JF_FLAG_NO_FOLD)) {
+            for (int j = i + 1; j < n_beams; j++) {
+                if (used[j]) continue;
+                double d = 0;
+                for (int k = 0; k < 3; k++) {
+                    double e = beams[3 * i + k] + beams[3 * j + k];
+                    d += e * e;
+                }
+                if (d < 1e-24) {
+                    used[j] = 1;
+                    w = 2.0;
+                    break;
+                }
+            }
+        }
+        rep.push_back(i);
+        wt.push_back(w);
+    }
+    c->n_dirs = (int)rep.size();
+    int quantum = JF_ELEM_LANES * 2;  // lanes x unroll
+    c->n_dirs_pad = (c->n_dirs + quantum - 1) / quantum * quantum;
+    // layout: (JF_NTAB/2) planes of n_dirs_pad double2
+    std::vector<double> tab((size_t)JF_NTAB * c->n_dirs_pad, 0.0);
+    auto put = [&](int comp, int b, double v) { tab[((size_t)(comp >> 1) * c->n_dirs_pad + b) * 2 + (comp & 1)] = v; };
+    for (int b = 0; b < c->n_dirs_pad; b++) {
+        double s[3] = {1.0, 0.0, 0.0}, w = 0.0;  // padding: harmless direction with zero weight
+        if (b < c->n_dirs) {
+            for (int k = 0; k < 3; k++) s[k] = beams[3 * rep[b] + k];
+            w = wt[b];
+        }
+        put(0, b, s[0] * s[0]);
+        put(1, b, s[1] * s[1]);
+        put(2, b, s[2] * s[2]);
+        put(3, b, s[0] * s[1]);
+        put(4, b, s[0] * s[2]);
+        put(5, b, s[1] * s[2]);
+        for (int ex = 4; ex >= 0; ex--)
+            for (int ey = 4 - ex; ey >= 0; ey--) {
+                int ez = 4 - ex - ey;
+                double v = 1.0;
+                for (int q = 0; q < ex; q++) v *= s[0];
+                for (int q = 0; q < ey; q++) v *= s[1];
+                for (int q = 0; q < ez; q++) v *= s[2];
+                put(6 + mono_id(ex, ey), b, v);
+            }
+        put(21, b, w);
+    }
+    if (jf_dev_alloc(c, &c->d_dirtab, tab.size())) return JF_ERR_CUDA;
+    JF_CUDA(cudaMemcpy(c->d_dirtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// node adjacency (sorted, unique, including self)
+// ------------------------------------------------------------------------------------------------
+static void build_adjacency(int64_t N, int64_t T, const int32_t *tets, std::vector<int64_t> &ptr,
+                            std::vector<int32_t> &adj) {
+    std::vector<int64_t> cnt(N + 1, 0);
+    for (int64_t t = 0; t < T; t++)
+        for (int m = 0; m < 4; m++) cnt[tets[4 * t + m] + 1] += 4;
+    for (int64_t i = 0; i < N; i++) cnt[i + 1] += cnt[i];
+    std::vector<int32_t> raw((size_t)cnt[N]);
+    std::vector<int64_t> fill(cnt.begin(), cnt.end() - 1);
+    for (int64_t t = 0; t < T; t++)
+        for (int m = 0; m < 4; m++)
+            for (int r = 0; r < 4; r++) raw[fill[tets[4 * t + m]]++] = tets[4 * t + r];
+    ptr.assign(N + 1, 0);
+    for (int64_t i = 0; i < N; i++) {
+        auto a = raw.begin() + cnt[i], b = raw.begin() + cnt[i + 1];
+        std::sort(a, b);
+        ptr[i + 1] = std::unique(a, b) - a;
+    }
+    for (int64_t i = 0; i < N; i++) ptr[i + 1] += ptr[i];
+    adj.resize((size_t)ptr[N]);
+    for (int64_t i = 0; i < N; i++) std::copy(raw.begin() + cnt[i], raw.begin() + cnt[i] + (ptr[i + 1] - ptr[i]), adj.begin() + ptr[i]);
+}
+
+// Cuthill-McKee over the free nodes, then degree-sort inside windows so SELL slices pad little
+static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int64_t> &ptr,
+                        const std::vector<int32_t> &adj) {
+    int64_t N = c->N;
+    std::vector<int32_t> order;
+    order.reserve(N);
+    if (c->flags & JF_FLAG_NO_REORDER) {
+        for (int64_t i = 0; i < N; i++)
+            if (movable[i]) order.push_back((int32_t)i);
+    } else {
+        std::vector<int32_t> deg(N, 0);
+        for (int64_t i = 0; i < N; i++)
+            if (movable[i])
+                for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) deg[i] += movable[adj[k]] ? 1 : 0;
+        std::vector<char> seen(N, 0);
+        // seeds in order of increasing degree (first unvisited wins)
+        std::vector<int32_t> seeds;
+        for (int64_t i = 0; i < N; i++)
+            if (movable[i]) seeds.push_back((int32_t)i);
+        std::stable_sort(seeds.begin(), seeds.end(), [&](int32_t a, int32_t b) { return deg[a] < deg[b]; });
+        std::vector<int32_t> nb;
+        for (int32_t seed : seeds) {
+            if (seen[seed]) continue;
+            seen[seed] = 1;
+            size_t head = order.size();
+            order.push_back(seed);
+            while (head < order.size()) {
+                int32_t u = order[head++];
+                nb.clear();
+                for (int64_t k = ptr[u]; k < ptr[u + 1]; k++) {
+                    int32_t v = adj[k];
+                    if (movable[v] && !seen[v]) {
+                        seen[v] = 1;
+                        nb.push_back(v);
+                    }
+                }
+                std::stable_sort(nb.begin(), nb.end(), [&](int32_t a, int32_t b) { return deg[a] < deg[b]; });
+                order.insert(order.end(), nb.begin(), nb.end());
+            }
+        }
+        const size_t window = 1024;
+        for (size_t a = 0; a < order.size(); a += window) {
+            size_t b = std::min(order.size(), a + window);
+            std::stable_sort(order.begin() + a, order.begin() + b, [&](int32_t x, int32_t y) { return deg[x] > deg[y]; });
+        }
+    }
+    c->Nf = (int64_t)order.size();
+    for (int64_t i = 0; i < N; i++)
+        if (!movable[i]) order.push_back((int32_t)i);
+    c->node_new2old = order;
+    c->node_old2new.assign(N, 0);
+    for (int64_t i = 0; i < N; i++) c->node_old2new[order[i]] = (int32_t)i;
+}
+
+template <typename Tp>
+static int upload(jf_ctx *c, Tp **dst, const std::vector<Tp> &src) {
+    if (jf_dev_alloc(c, dst, src.size())) return JF_ERR_CUDA;
+    if (!src.empty()) JF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, const uint8_t *movable,
+                       const double *beams, int n_beams) {
+    const int64_t N = c->N, T = c->T;
+    for (int64_t i = 0; i < 4 * T; i++)
+        if (tets_in[i] < 0 || tets_in[i] >= N) {
+            jf_set_error("tetrahedron %lld references node %d outside [0,%lld)", (long long)(i / 4), tets_in[i], (long long)N);
+            return JF_ERR_ARG;
+        }
+    int rc = build_dirtab(c, beams, n_beams);
+    if (rc) return rc;
+
+    std::vector<int64_t> aptr;
+    std::vector<int32_t> adj;
+    build_adjacency(N, T, tets_in, aptr, adj);
+    order_nodes(c, movable, aptr, adj);
+    const int64_t Nf = c->Nf;
+    const std::vector<int32_t> &o2n = c->node_old2new;
+
+    // tets: renumber, order by smallest new node id (keeps U gathers and K_el reads local)
+    std::vector<int32_t> torder(T);
+    std::iota(torder.begin(), torder.end(), 0);
+    if (!(c->flags & JF_FLAG_NO_REORDER)) {
+        std::vector<int32_t> key(T);
+        for (int64_t t = 0; t < T; t++) {
+            int32_t k = o2n[tets_in[4 * t]];
+            for (int m = 1; m < 4; m++) k = std::min(k, o2n[tets_in[4 * t + m]]);
+            key[t] = k;
+        }
+        std::stable_sort(torder.begin(), torder.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    }
+    c->tet_new2old = torder;
+    std::vector<int32_t> tets((size_t)4 * T);
+    for (int64_t t = 0; t < T; t++)
+        for (int m = 0; m < 4; m++) tets[4 * t + m] = o2n[tets_in[4 * (int64_t)torder[t] + m]];
+    std::vector<double> xyz((size_t)3 * N);
+    for (int64_t i = 0; i < N; i++)
+        for (int k = 0; k < 3; k++) xyz[3 * i + k] = nodes[3 * (int64_t)c->node_new2old[i] + k];
+
+    // shape tensors Phi = Chi * B^-1, V = |det B|/6  
+    std::vector<double> phi((size_t)12 * T), vol(T);
+    for (int64_t t = 0; t < T; t++) {
+        const int32_t *n = &tets[4 * t];
+        double B[3][3];
+        for (int col = 0; col < 3; col++)
+            for (int i = 0; i < 3; i++) B[i][col] = xyz[3 * (int64_t)n[col + 1] + i] - xyz[3 * (int64_t)n[0] + i];
+        double det = B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[2][1]) - B[0][1] * (B[1][0] * B[2][2] - B[1][2] * B[2][0]) +
+                     B[0][2] * (B[1][0] * B[2][1] - B[1][1] * B[2][0]);
+        if (det == 0.0 || !isfinite(det)) {
+            jf_set_error("tetrahedron %d is degenerate (zero volume)", (int)torder[t]);
+            return JF_ERR_ARG;
+        }
+        double inv[3][3];
+        inv[0][0] = (B[1][1] * B[2][2] - B[1][2] * B[2][1]) / det;
+        inv[0][1] = (B[0][2] * B[2][1] - B[0][1] * B[2][2]) / det;
+        inv[0][2] = (B[0][1] * B[1][2] - B[0][2] * B[1][1]) / det;
+        inv[1][0] = (B[1][2] * B[2][0] - B[1][0] * B[2][2]) / det;
+        inv[1][1] = (B[0][0] * B[2][2] - B[0][2] * B[2][0]) / det;
+        inv[1][2] = (B[0][2] * B[1][0] - B[0][0] * B[1][2]) / det;
+        inv[2][0] = (B[1][0] * B[2][1] - B[1][1] * B[2][0]) / det;
+        inv[2][1] = (B[0][1] * B[2][0] - B[0][0] * B[2][1]) / det;
+        inv[2][2] = (B[0][0] * B[1][1] - B[0][1] * B[1][0]) / det;
+        vol[t] = fabs(det) / 6.0;
+        double *P = &phi[12 * t];
+        for (int j = 0; j < 3; j++) {
+            P[j] = -(inv[0][j] + inv[1][j] + inv[2][j]);
+            P[3 + j] = inv[0][j];
+            P[6 + j] = inv[1][j];
+            P[9 + j] = inv[2][j];
+        }
+    }
+
+    // SELL-32 pattern over free rows / free columns, in new numbering
+    c->n_slices = (Nf + JF_SLICE - 1) / JF_SLICE;
+    c->Nf_pad = c->n_slices * JF_SLICE;
+    std::vector<int64_t> rptr(Nf + 1, 0);   // free-neighbour lists in new ids, sorted
+    std::vector<int32_t> rcol;
+    rcol.reserve((size_t)aptr[N]);
+    {
+        std::vector<int32_t> tmp;
+        for (int64_t i = 0; i < Nf; i++) {
+            int32_t old = c->node_new2old[i];
+            tmp.clear();
+            for (int64_t k = aptr[old]; k < aptr[old + 1]; k++) {
+                int32_t v = o2n[adj[k]];
+                if (v < Nf) tmp.push_back(v);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            rcol.insert(rcol.end(), tmp.begin(), tmp.end());
+            rptr[i + 1] = (int64_t)rcol.size();
+        }
+    }
+    c->n_blocks = (int64_t)rcol.size();
+    std::vector<int32_t> slice_ptr(c->n_slices + 1, 0);
+    for (int64_t k = 0; k < c->n_slices; k++) {
+        int64_t w = 0;
+        for (int64_t i = k * JF_SLICE; i < std::min<int64_t>(Nf, (k + 1) * JF_SLICE); i++) w = std::max(w, rptr[i + 1] - rptr[i]);
+        int64_t next = (int64_t)slice_ptr[k] + w * JF_SLICE;
+        if (next * 9 > 2000000000LL) {
+            jf_set_error("mesh too large for 32-bit slot offsets");
+            return JF_ERR_ARG;
+        }
+        slice_ptr[k + 1] = (int32_t)next;
+    }
+    c->n_slots = slice_ptr[c->n_slices];
+    std::vector<int32_t> sell_col((size_t)c->n_slots);
+    for (int64_t k = 0; k < c->n_slices; k++) {
+        int64_t w = (slice_ptr[k + 1] - slice_ptr[k]) / JF_SLICE;
+        for (int64_t j = 0; j < w; j++)
+            for (int lane = 0; lane < JF_SLICE; lane++) {
+                int64_t row = k * JF_SLICE + lane;
+                int32_t col = (int32_t)std::min<int64_t>(row, Nf - 1);  // padding: zero block on a valid column
+                if (row < Nf && j < rptr[row + 1] - rptr[row]) col = rcol[rptr[row] + j];
+                sell_col[slice_ptr[k] + j * JF_SLICE + lane] = col;
+            }
+    }
+    auto slot_of = [&](int32_t row, int32_t col) -> int64_t {
+        const int32_t *a = &rcol[rptr[row]], *b = &rcol[rptr[row + 1]];
+        const int32_t *hit = std::lower_bound(a, b, col);
+        return (int64_t)slice_ptr[row / JF_SLICE] + (hit - a) * JF_SLICE + row % JF_SLICE;
+    };
+    // gather lists for the stiffness: slot <- ((t*10+pair)*2+transpose), ascending t
+    static const int pair_of[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+    if ((int64_t)T * 20 > 2000000000LL) {
+        jf_set_error("mesh too large for 32-bit element offsets");
+        return JF_ERR_ARG;
+    }
+    std::vector<int32_t> cptr((size_t)c->n_slots + 1, 0);
+    for (int64_t t = 0; t < T; t++)
+        for (int m = 0; m < 4; m++) {
+            int32_t a = tets[4 * t + m];
+            if (a >= Nf) continue;
+            for (int r = 0; r < 4; r++) {
+                int32_t b = tets[4 * t + r];
+                if (b >= Nf) continue;
+                cptr[slot_of(a, b) + 1]++;
+            }
+        }
+    for (int64_t q = 0; q < c->n_slots; q++) cptr[q + 1] += cptr[q];
+    std::vector<int32_t> csrc((size_t)cptr[c->n_slots]);
+    {
+        std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+        for (int64_t t = 0; t < T; t++)
+            for (int m = 0; m < 4; m++) {
+                int32_t a = tets[4 * t + m];
+                if (a >= Nf) continue;
+                for (int r = 0; r < 4; r++) {
+                    int32_t b = tets[4 * t + r];
+                    if (b >= Nf) continue;
+                    int tr = m > r;
+                    csrc[fill[slot_of(a, b)]++] = (int32_t)(((t * 10 + pair_of[m][r]) << 1) | tr);
+                }
+            }
+    }
+    // gather lists for nodal forces: node <- (t*4+m)
+    std::vector<int32_t> fptr(N + 1, 0);
+    for (int64_t i = 0; i < 4 * T; i++) fptr[tets[i] + 1]++;
+    for (int64_t i = 0; i < N; i++) fptr[i + 1] += fptr[i];
+    std::vector<int32_t> fsrc((size_t)4 * T);
+    {
+        std::vector<int32_t> fill(fptr.begin(), fptr.end() - 1);
+        for (int64_t i = 0; i < 4 * T; i++) fsrc[fill[tets[i]]++] = (int32_t)i;
+    }
+
+    if ((rc = upload(c, &c->d_tets, tets))) return rc;
+    if ((rc = upload(c, &c->d_nodes, xyz))) return rc;
+    if ((rc = upload(c, &c->d_phi, phi))) return rc;
+    if ((rc = upload(c, &c->d_vol, vol))) return rc;
+    if ((rc = upload(c, &c->d_slice_ptr, slice_ptr))) return rc;
+    if ((rc = upload(c, &c->d_sell_col, sell_col))) return rc;
+    if ((rc = upload(c, &c->d_contrib_ptr, cptr))) return rc;
+    if ((rc = upload(c, &c->d_contrib_src, csrc))) return rc;
+    if ((rc = upload(c, &c->d_fn_ptr, fptr))) return rc;
+    if ((rc = upload(c, &c->d_fn_src, fsrc))) return rc;
+    c->h_rowlen.resize(Nf);
+    for (int64_t i = 0; i < Nf; i++) c->h_rowlen[i] = (int32_t)(rptr[i + 1] - rptr[i]);
+    c->h_sell_col.swap(sell_col);
+    c->h_slice_ptr.swap(slice_ptr);
+    return 0;
+}

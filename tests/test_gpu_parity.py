@@ -1,0 +1,184 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+from conftest import COLLAGEN12, LINEAR, FIBRIN, BATCH_A, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_U(case, scale, seed=0):
+    rng = np.random.default_rng(seed)
+    r = np.linalg.norm(case["coords"], axis=1)
+    U = rng.normal(size=case["coords"].shape) * (scale * r)[:, None]
+    U[~case["movable"]] = 0.0
+    return U
+
+
+@pytest.mark.parametrize("mat", [COLLAGEN12, LINEAR, FIBRIN, BATCH_A])
+@pytest.mark.parametrize("scale", [1e-7, 3e-3, 5e-2])
+def test_element_quantities_match_oracle(mat, scale, beams):
+    from jointforces_b200 import _lib
+    from oracle import c_oracle
+    case = make_case(0.667)
+    U = _random_U(case, scale)
+    E0, f0, K0 = c_oracle.element_eval(case["coords"], case["tets"], U, beams, mat)
+    with _lib.Context(case["coords"], case["tets"], case["movable"], beams=beams) as ctx:
+        ctx.set_material(*mat)
+        ctx.set_displacements(U)
+        ctx.evaluate()
+        E, f, K = ctx.element_quantities()
+    # per-tet relative to the largest entry of that tet (entries that cancel to ~0 carry no information)
+    def rel(a, b):
+        a = a.reshape(len(a), -1); b = b.reshape(len(b), -1)
+        return np.max(np.abs(a - b).max(1) / np.maximum(np.abs(b).max(1), 1e-300))
+    assert rel(K, K0) < 1e-11
+    assert rel(f, f0) < 1e-9 or np.abs(f - f0).max() < 1e-12 * np.abs(K0).max() * np.abs(U).max()
+    assert np.abs(E - E0).max() <= 1e-10 * np.abs(E0).max() + 1e-300
+
+
+@pytest.mark.parametrize("mat", [COLLAGEN12, LINEAR])
+def test_assembly_matches_oracle(mat, beams):
+    from jointforces_b200 import _lib
+    from oracle import c_oracle
+    case = make_case(0.667)
+    U = _random_U(case, 1e-2, seed=3)
+    e0, f0, K0 = c_oracle.assemble(case["coords"], case["tets"], case["movable"], U, beams, mat)
+    with _lib.Context(case["coords"], case["tets"], case["movable"], beams=beams) as ctx:
+        ctx.set_material(*mat)
+        ctx.set_targets(case["f_target"])
+        ctx.set_displacements(U)
+        ctx.evaluate()
+        e, r2, f2 = ctx.energy()
+        f = ctx.forces()
+        K = ctx.stiffness_csr()
+    assert abs(e - e0) < 1e-11 * abs(e0)
+    assert np.abs(f - f0).max() < 1e-10 * np.abs(f0).max()
+    # the library drops the columns of fixed nodes (they multiply zeros in CG); compare free x free
+    free = np.repeat(case["movable"], 3)
+    D = (K - K0)[free][:, free]
+    assert abs(D).max() < 1e-11 * abs(K0).max()
+    assert K[~free].nnz == 0
+    m = case["movable"]
+    assert abs(f2 - np.sum(f0[m] ** 2)) < 1e-10 * f2
+    assert abs(r2 - np.sum((f0[m] - case["f_target"][m]) ** 2)) < 1e-10 * r2
+
+
+def test_cg_matches_oracle(beams):
+    from jointforces_b200 import _lib
+    from oracle import c_oracle
+    from oracle.saeno_oracle import cg
+    case = make_case(0.667)
+    U = _random_U(case, 1e-3, seed=5)
+    _, f0, K0 = c_oracle.assemble(case["coords"], case["tets"], case["movable"], U, beams, COLLAGEN12)
+    b = f0 - case["f_target"]
+    b[~case["movable"]] = 0
+    x0, it0 = cg(K0, b.ravel(), maxiter=3 * len(b), tol=1e-5, return_iterations=True)
+    x1, it1 = cg(K0, b.ravel(), maxiter=3 * len(b), tol=1e-20, return_iterations=True)
+    with _lib.Context(case["coords"], case["tets"], case["movable"], beams=beams) as ctx:
+        ctx.set_material(*COLLAGEN12)
+        ctx.set_targets(case["f_target"])
+        ctx.set_displacements(U)
+        ctx.evaluate()
+        it = ctx.cg(1e-5)
+        x = ctx.cg_solution()
+        it_t = ctx.cg(1e-20)
+        x_t = ctx.cg_solution()
+    assert abs(int(it[0]) - it0) <= 1
+    assert np.linalg.norm(x.ravel() - x0) < 5e-3 * np.linalg.norm(x0)
+    assert np.linalg.norm(x_t.ravel() - x1) < 1e-7 * np.linalg.norm(x1)
+    assert np.all(x[~case["movable"]] == 0)
+
+
+@pytest.mark.parametrize("mat,pressure,step", [(COLLAGEN12, 100.0, 0.0033), (LINEAR, 1.0, 0.066), (BATCH_A, 1000.0, 0.0033)])
+def test_relaxation_matches_oracle(mat, pressure, step, beams):
+    """The BASELINE tolerance: relaxed displacements within 1e-4 relative L2 of the oracle."""
+    from jointforces_b200 import _lib
+    from oracle import c_oracle
+    case = make_case(0.667, pressure)
+    ref = c_oracle.relax(case["coords"], case["tets"], case["movable"], case["f_target"], np.zeros_like(case["coords"]),
+                         beams, mat, step, 600, 0.01, nthreads=1)
+    out = _lib.solve_boundarycondition(case["coords"], case["tets"], case["movable"], case["f_target"],
+                                       np.zeros_like(case["coords"]), mat, step, 600, 0.01, beams=beams)
+    assert out["n_iter"] == ref["n_iter"]
+    err = np.linalg.norm(out["U"] - ref["U"]) / np.linalg.norm(ref["U"])
+    assert err < 1e-4, err
+    assert np.allclose(out["relrec"][:, 1], ref["relrec"][:, 1], rtol=1e-4)
+    assert np.abs(out["cg_iters"].astype(int) - ref["cg_iters"]).max() <= 3
+    assert np.abs(out["forces"] - ref["forces"]).max() < 1e-3 * np.abs(ref["forces"]).max()
+
+
+def test_relaxation_tight_cg_matches_oracle_closely(beams):
+    """With CG converged hard the iteration-count sensitivity disappears: agreement ~1e-9."""
+    from jointforces_b200 import _lib
+    from oracle.saeno_oracle import Solver, SemiAffineFiberMaterial, cg
+    import oracle.saeno_oracle as so
+    case = make_case(0.667, 100.0)
+    S = Solver()
+    S.set_material_model(SemiAffineFiberMaterial(*COLLAGEN12))
+    S.set_nodes(case["coords"]); S.set_tetrahedra(case["tets"])
+    S.set_boundary_condition(case["bc"]["displacement"], case["bc"]["forces"])
+    S._prepare(); S._update_glo_f_and_K()
+    m = S.mesh
+    for _ in range(5):
+        ff = m.forces - m.forces_target
+        ff[~m.movable] = 0
+        uu = cg(S.K_glo, ff.ravel(), maxiter=3 * len(ff), tol=1e-22).reshape(ff.shape)
+        m.displacements[m.movable] += 0.05 * uu[m.movable]
+        S._update_glo_f_and_K()
+    with _lib.Context(case["coords"], case["tets"], case["movable"], beams=beams) as ctx:
+        ctx.set_material(*COLLAGEN12)
+        ctx.set_targets(case["f_target"])
+        ctx.set_displacements(np.zeros_like(case["coords"]))
+        relrec, cgit, n = ctx.relax(0.05, 5, 0.0, cg_tol=1e-22)
+        U = ctx.displacements()
+    assert n[0] == 5
+    assert np.linalg.norm(U - m.displacements) / np.linalg.norm(U) < 1e-8
+
+
+def test_lockstep_batch_equals_single_solves(beams):
+    from jointforces_b200 import _lib
+    pressures = [1.0, 100.0, 3000.0]
+    cases = [make_case(0.667, p) for p in pressures]
+    c0 = cases[0]
+    singles = [_lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
+                                            COLLAGEN12, 0.0033, 600, 0.01, beams=beams) for c in cases]
+    with _lib.Context(c0["coords"], c0["tets"], c0["movable"], n_sys=3, beams=beams) as ctx:
+        ctx.set_material(*COLLAGEN12)
+        for s, c in enumerate(cases):
+            ctx.set_targets(c["f_target"], s)
+            ctx.set_displacements(np.zeros_like(c["coords"]), s)
+        relrec, cgit, n = ctx.relax(0.0033, 600, 0.01)
+        for s in range(3):
+            assert n[s] == singles[s]["n_iter"]
+            assert np.array_equal(ctx.displacements(s), singles[s]["U"])  # same kernels, same order: bitwise
+            assert np.array_equal(relrec[s], singles[s]["relrec"])
+
+
+def test_bitwise_reproducible(beams):
+    from jointforces_b200 import _lib
+    c = make_case(0.667, 300.0)
+    a = _lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
+                                     COLLAGEN12, 0.0033, 40, 0.01, beams=beams)
+    b = _lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
+                                     COLLAGEN12, 0.0033, 40, 0.01, beams=beams)
+    assert np.array_equal(a["U"], b["U"]) and np.array_equal(a["relrec"], b["relrec"])
+
+
+def test_reordering_and_folding_are_transparent(beams):
+    """Internal renumbering / antipodal folding must not change results beyond rounding."""
+    from jointforces_b200 import _lib
+    c = make_case(0.667, 100.0)
+    U = _random_U(c, 1e-2, seed=9)
+    outs = []
+    for flags in (0, _lib.JF_FLAG_NO_REORDER | _lib.JF_FLAG_NO_FOLD):
+        with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams, flags=flags) as ctx:
+            ctx.set_material(*COLLAGEN12)
+            ctx.set_targets(c["f_target"])
+            ctx.set_displacements(U)
+            ctx.evaluate()
+            outs.append((ctx.forces(), ctx.stiffness_csr(), ctx.energy()[0], ctx.info()))
+    assert outs[0][3]["n_dirs"] == 172 and outs[1][3]["n_dirs"] == 286
+    assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-11 * np.abs(outs[1][0]).max()
+    assert abs(outs[0][1] - outs[1][1]).max() < 1e-11 * abs(outs[1][1]).max()
+    assert abs(outs[0][2] - outs[1][2]) < 1e-12 * abs(outs[1][2])
