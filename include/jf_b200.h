@@ -71,6 +71,8 @@ int jf_set_targets(jf_ctx *ctx, int sys, const double *f_target);
  * value, free nodes the start value).  NaN entries are read as 0. */
 int jf_set_displacements(jf_ctx *ctx, int sys, const double *U);
 int jf_get_displacements(jf_ctx *ctx, int sys, double *U);
+/* device-side reset of U to what the last jf_set_displacements stored (sys = -1: all systems) */
+int jf_restore_displacements(jf_ctx *ctx, int sys);
 /* internal nodal forces f (n_nodes,3) of the last evaluation (Solver.mesh.forces, simulation.py:255) */
 int jf_get_forces(jf_ctx *ctx, int sys, double *f);
 
@@ -113,6 +115,9 @@ typedef struct jf_stats {
     int64_t cg_launches;    /* CG kernel launches                     */
     int64_t kernel_launches;/* all kernels launched                   */
     int64_t newton_steps;   /* sum over systems                       */
+    double ms_relax;        /* device time from the first to the last kernel of jf_relax calls */
+    int64_t bytes_h2d;      /* host->device bytes copied (incl. setup uploads)  */
+    int64_t bytes_d2h;      /* device->host bytes copied                        */
 } jf_stats;
 int jf_get_stats(jf_ctx *ctx, jf_stats *out);
 int jf_reset_stats(jf_ctx *ctx);

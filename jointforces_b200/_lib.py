@@ -20,7 +20,7 @@ JF_FLAG_NO_FOLD = 2
 # every symbol include/jf_b200.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "jf_last_error", "jf_version", "jf_device_count", "jf_ctx_create", "jf_ctx_destroy", "jf_set_material",
-    "jf_set_targets", "jf_set_displacements", "jf_get_displacements", "jf_get_forces", "jf_evaluate", "jf_get_energy",
+    "jf_set_targets", "jf_set_displacements", "jf_get_displacements", "jf_restore_displacements", "jf_get_forces", "jf_evaluate", "jf_get_energy",
     "jf_get_element_quantities", "jf_get_stiffness_blocks", "jf_cg", "jf_get_cg_solution", "jf_relax", "jf_get_stats",
     "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64",
 ]
@@ -33,7 +33,8 @@ class JFError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("ms_element", C.c_double), ("ms_assembly", C.c_double), ("ms_cg", C.c_double), ("ms_setup", C.c_double),
                 ("tet_updates", C.c_int64), ("cg_iterations", C.c_int64), ("cg_launches", C.c_int64),
-                ("kernel_launches", C.c_int64), ("newton_steps", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("newton_steps", C.c_int64), ("ms_relax", C.c_double),
+                ("bytes_h2d", C.c_int64), ("bytes_d2h", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -77,6 +78,7 @@ def load():
     L.jf_set_targets.argtypes = [_vp, C.c_int, _dp]
     L.jf_set_displacements.argtypes = [_vp, C.c_int, _dp]
     L.jf_get_displacements.argtypes = [_vp, C.c_int, _dp]
+    L.jf_restore_displacements.argtypes = [_vp, C.c_int]
     L.jf_get_forces.argtypes = [_vp, C.c_int, _dp]
     L.jf_evaluate.argtypes = [_vp]
     L.jf_get_energy.argtypes = [_vp, C.c_int] + [C.POINTER(C.c_double)] * 3
@@ -153,6 +155,9 @@ class Context:
 
     def set_displacements(self, U, sys=0):
         check(self._L.jf_set_displacements(self._h, int(sys), np.ascontiguousarray(U, dtype=np.float64)))
+
+    def restore_displacements(self, sys=-1):
+        check(self._L.jf_restore_displacements(self._h, int(sys)))
 
     # --- getters ---------------------------------------------------------------------------------
     def displacements(self, sys=0):

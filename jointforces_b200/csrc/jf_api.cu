@@ -67,7 +67,7 @@ static void ctx_free(jf_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     void *ptrs[] = {c->d_tets, c->d_nodes, c->d_phi, c->d_vol, c->d_dirtab, c->d_mat, c->d_state, c->d_U, c->d_ft, c->d_f,
-                    c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
+                    c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_partial,
                     c->d_barrier};
     for (void *p : ptrs)
@@ -128,6 +128,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if ((rc = jf_dev_alloc(c, &c->d_state, S))) break;
         if (cudaMallocHost((void **)&c->h_state, S * sizeof(jf_sys_state)) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "pinned", __FILE__, __LINE__); break; }
         if ((rc = jf_dev_alloc(c, &c->d_U, S * N * 3))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_U0, S * N * 3))) break;
         if ((rc = jf_dev_alloc(c, &c->d_ft, S * N * 3))) break;
         if ((rc = jf_dev_alloc(c, &c->d_f, S * N * 3))) break;
         if ((rc = jf_dev_alloc(c, &c->d_Et, S * T))) break;
@@ -145,6 +146,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if ((rc = jf_elem_configure(c))) break;
         if ((rc = jf_dev_alloc(c, &c->d_partial, 2 * S * (size_t)c->cg_grid))) break;
         cudaMemset(c->d_U, 0, S * N * 3 * sizeof(double));
+        cudaMemset(c->d_U0, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_ft, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_f, 0, S * N * 3 * sizeof(double));
         memset(c->h_state, 0, S * sizeof(jf_sys_state));
@@ -194,6 +196,7 @@ static int put_nodal(jf_ctx *c, double *dst_dev, int sys, const double *src, boo
     }
     JF_CUDA(cudaMemcpyAsync(dst_dev + (size_t)sys * c->N * 3, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     JF_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.bytes_h2d += (int64_t)(tmp.size() * sizeof(double));
     return JF_OK;
 }
 
@@ -201,6 +204,7 @@ static int get_nodal(jf_ctx *c, const double *src_dev, int sys, double *dst) {
     std::vector<double> tmp((size_t)c->N * 3);
     JF_CUDA(cudaMemcpyAsync(tmp.data(), src_dev + (size_t)sys * c->N * 3, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     JF_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.bytes_d2h += (int64_t)(tmp.size() * sizeof(double));
     for (int64_t i = 0; i < c->N; i++) {
         double *p = dst + 3 * (int64_t)c->node_new2old[i];
         for (int k = 0; k < 3; k++) p[k] = tmp[3 * i + k];
@@ -224,7 +228,21 @@ extern "C" int jf_set_displacements(jf_ctx *c, int sys, const double *U) {
     CHECK_SYS(c, sys);
     if (!U) { jf_set_error("null U"); return JF_ERR_ARG; }
     c->evaluated = false;
-    return put_nodal(c, c->d_U, sys, U, false);
+    int rc = put_nodal(c, c->d_U, sys, U, false);
+    if (rc) return rc;
+    JF_CUDA(cudaMemcpyAsync(c->d_U0 + (size_t)sys * c->N * 3, c->d_U + (size_t)sys * c->N * 3, (size_t)c->N * 3 * sizeof(double),
+                            cudaMemcpyDeviceToDevice, c->stream));
+    return JF_OK;
+}
+
+extern "C" int jf_restore_displacements(jf_ctx *c, int sys) {
+    CHECK_CTX(c);
+    if (sys != -1) CHECK_SYS(c, sys);
+    const size_t per = (size_t)c->N * 3;
+    const size_t off = sys < 0 ? 0 : (size_t)sys * per, cnt = sys < 0 ? per * c->n_sys : per;
+    JF_CUDA(cudaMemcpyAsync(c->d_U + off, c->d_U0 + off, cnt * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->evaluated = false;
+    return JF_OK;
 }
 
 extern "C" int jf_get_displacements(jf_ctx *c, int sys, double *U) {
@@ -258,6 +276,7 @@ static int evaluate_async(jf_ctx *c, bool timed) {
 static int fetch_state(jf_ctx *c) {
     JF_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, c->n_sys * sizeof(jf_sys_state), cudaMemcpyDeviceToHost, c->stream));
     JF_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.bytes_d2h += (int64_t)(c->n_sys * sizeof(jf_sys_state));
     return 0;
 }
 
@@ -425,6 +444,7 @@ extern "C" int jf_relax(jf_ctx *c, double step, int max_iter, double conv_crit, 
     const size_t stride = (size_t)(max_iter + 1) * 3;
     // all systems start active
     for (int s = 0; s < S; s++) c->h_state[s].active = 1;
+    JF_CUDA(cudaEventRecord(c->ev[5], c->stream));
     JF_CUDA(cudaMemcpyAsync(c->d_state, c->h_state, S * sizeof(jf_sys_state), cudaMemcpyHostToDevice, c->stream));
     if ((rc = evaluate_async(c, true))) return rc;
     if ((rc = fetch_state(c))) return rc;
@@ -481,6 +501,11 @@ extern "C" int jf_relax(jf_ctx *c, double step, int max_iter, double conv_crit, 
                 JF_CUDA(cudaMemcpyAsync(&c->d_state[s].active, &c->h_state[s].active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
         }
     }
+    JF_CUDA(cudaEventRecord(c->ev[6], c->stream));
+    JF_CUDA(cudaEventSynchronize(c->ev[6]));
+    float total = 0;
+    JF_CUDA(cudaEventElapsedTime(&total, c->ev[5], c->ev[6]));
+    c->stats.ms_relax += total;
     return JF_OK;
 }
 

@@ -65,6 +65,7 @@ struct jf_ctx {
     jf_sys_state *d_state = nullptr;
     jf_sys_state *h_state = nullptr;  // pinned mirror
     double *d_U = nullptr;         // (S,N,3)
+    double *d_U0 = nullptr;        // (S,N,3) start values kept for jf_restore_displacements
     double *d_ft = nullptr;        // (S,N,3) target forces (0 on fixed nodes)
     double *d_f = nullptr;         // (S,N,3) internal forces
     double *d_Et = nullptr;        // (S,T) per-tet energy

@@ -102,6 +102,7 @@ static int build_dirtab(jf_ctx *c, const double *beams, int n_beams) {
     }
     if (jf_dev_alloc(c, &c->d_dirtab, tab.size())) return JF_ERR_CUDA;
     JF_CUDA(cudaMemcpy(c->d_dirtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->stats.bytes_h2d += (int64_t)(tab.size() * sizeof(double));
     return 0;
 }
 
@@ -188,6 +189,7 @@ template <typename Tp>
 static int upload(jf_ctx *c, Tp **dst, const std::vector<Tp> &src) {
     if (jf_dev_alloc(c, dst, src.size())) return JF_ERR_CUDA;
     if (!src.empty()) JF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    c->stats.bytes_h2d += (int64_t)(src.size() * sizeof(Tp));
     return 0;
 }
 
