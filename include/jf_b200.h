@@ -41,6 +41,7 @@ enum jf_status {
 /* jf_ctx_create flags */
 #define JF_FLAG_NO_REORDER 1u /* keep the caller's node/tet order (default: locality reordering) */
 #define JF_FLAG_NO_FOLD 2u    /* do not merge antipodal directions (default: merge, exact)        */
+#define JF_FLAG_NO_RESIDENT 4u /* never use the shared-memory-resident CG kernel (testing)        */
 
 const char *jf_last_error(void);
 int jf_version(void);
@@ -127,6 +128,7 @@ typedef struct jf_info {
     int64_t n_nodes, n_free, n_tets, n_blocks /* non-zero 3x3 blocks */, n_slots /* incl. SELL padding */;
     int32_t n_sys, n_dirs /* directions after folding */, n_beams, sm_count, cg_grid, cg_block, elem_grid, elem_block;
     int64_t bytes_device;
+    int32_t cg_resident /* 1: matrix slices live in shared memory for the whole CG solve */, cg_wmax;
 } jf_info;
 int jf_get_info(jf_ctx *ctx, jf_info *out);
 

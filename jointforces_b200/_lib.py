@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libjf_b200.so")
 
 JF_FLAG_NO_REORDER = 1
 JF_FLAG_NO_FOLD = 2
+JF_FLAG_NO_RESIDENT = 4
 
 # every symbol include/jf_b200.h declares (tests check the library exports each of them)
 SYMBOLS = [
@@ -44,7 +45,8 @@ class Info(C.Structure):
     _fields_ = [("n_nodes", C.c_int64), ("n_free", C.c_int64), ("n_tets", C.c_int64), ("n_blocks", C.c_int64),
                 ("n_slots", C.c_int64), ("n_sys", C.c_int32), ("n_dirs", C.c_int32), ("n_beams", C.c_int32),
                 ("sm_count", C.c_int32), ("cg_grid", C.c_int32), ("cg_block", C.c_int32), ("elem_grid", C.c_int32),
-                ("elem_block", C.c_int32), ("bytes_device", C.c_int64)]
+                ("elem_block", C.c_int32), ("bytes_device", C.c_int64), ("cg_resident", C.c_int32),
+                ("cg_wmax", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

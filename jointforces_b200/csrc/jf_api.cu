@@ -144,7 +144,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if (rc) break;
         if ((rc = jf_cg_configure(c))) break;
         if ((rc = jf_elem_configure(c))) break;
-        if ((rc = jf_dev_alloc(c, &c->d_partial, 2 * S * (size_t)c->cg_grid))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_partial, 4 * S * (size_t)c->cg_grid))) break;  // (2, S, grid) 16-byte slots
         cudaMemset(c->d_U, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_U0, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_ft, 0, S * N * 3 * sizeof(double));
@@ -542,6 +542,8 @@ extern "C" int jf_get_info(jf_ctx *c, jf_info *o) {
     o->elem_grid = c->elem_grid;
     o->elem_block = JF_ELEM_BLOCK;
     o->bytes_device = c->bytes_device;
+    o->cg_resident = c->cg_resident;
+    o->cg_wmax = c->cg_wmax;
     return JF_OK;
 }
 

@@ -4,27 +4,37 @@
 //
 // Arithmetic is plain Hestenes-Stiefel in saenopy's order -- alpha = resid/(p.Ap); x += alpha p;
 // r -= alpha Ap; rsnew = r.r; stop when rsnew < tol*normb; beta = rsnew/resid; p = r + beta p --
-// for all systems of the context in lockstep.  Two grid barriers per iteration:
+// for all systems of the context in lockstep.  Two grid-wide synchronisations per iteration:
 //   phase A  Ap = K p, with p_j = r_j + beta*pold_j formed on the fly while gathering (so the
-//            "p = r + beta p" pass and its barrier disappear; own-row p is written to the other
-//            p buffer), fused p.Ap partials
+//            "p = r + beta p" pass and its barrier disappear; own-row p goes to the other p
+//            buffer), fused p.Ap partials
 //   phase B  x += alpha p, r -= alpha Ap, fused r.r partials
-// Dot products are reduced in a fixed order (lane -> warp shuffle tree -> per-CTA slot -> every
-// CTA sums the slots in the same order), so results are bitwise reproducible for a given grid.
-// The final pass applies U += step*x on the free nodes and reduces du (A12).
 //
-// Matrix: SELL-32 3x3 blocks (jf_assembly.cu); one thread owns one block row, so every matrix
-// load of a warp is a 256-byte line.  Vectors are (row,4) doubles so a gathered node is one
-// 32-byte sector.  HBM-bound for matrices beyond L2 (126 MB), barrier/latency-bound below.
+// Grid synchronisation and the dot products are ONE primitive (grid_allreduce): every CTA
+// publishes its partial sums in flag-carrying 16-byte slots (each 8-byte half holds 32 data bits
+// and the 32-bit epoch, so a half-written slot can never be mistaken for data), every CTA polls
+// all slots and adds them in the same fixed order.  That is a barrier and an all-reduce in one
+// L2 round trip, and results are bitwise reproducible for a given grid -- no atomics anywhere.
+//
+// Two kernels share that skeleton:
+//   jf_cg_resident_kernel  every (system, 32-row slice) has its own warp for the whole solve: the
+//                          slice's matrix blocks and column indices are staged ONCE in shared
+//                          memory, x/r/p/Ap of the row live in registers, and the only global
+//                          traffic per iteration is the neighbour gather of r and p.  Used when
+//                          n_sys * n_slices <= #SM * warps-that-fit (config 2: 536 slices, 18 MB
+//                          of blocks spread over the 148 SMs' shared memory).
+//   jf_cg_stream_kernel    larger meshes / wider batches: matrix streamed from L2/HBM in SELL-32
+//                          order (every warp load is a 256-byte line), vectors in global memory.
+//
+// Matrix: SELL-32 3x3 blocks (jf_assembly.cu); one thread owns one block row.  Vectors are
+// (row,4) doubles so a gathered node is one 32-byte sector.
 #include <cooperative_groups.h>
 
 #include "jf_internal.h"
 
-namespace cg = cooperative_groups;
-
 namespace {
 
-constexpr int WARPS = JF_CG_BLOCK / 32;
+constexpr int MAXW = 32;  // warps per CTA upper bound
 
 struct CgArgs {
     const int32_t *slice_ptr;
@@ -32,11 +42,12 @@ struct CgArgs {
     const double *val;
     const double *b;
     double *x, *r, *p0, *p1, *Ap;
-    double *partial;  // (2, n_sys, grid)
+    ulonglong2 *slots;  // (2, n_sys, grid) flag-carrying partial sums
     jf_sys_state *state;
     double *U;
     long long N, Nf, Nf_pad, n_slices, n_slots;
     int n_sys;
+    int wmax;  // widest slice (resident kernel: shared-memory stride)
     double tol;
     long long maxiter;
     double step;
@@ -49,57 +60,253 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// s_warp[s][warp] -> partial[s][block]; every warp handles systems warp, warp+WARPS, ...
-__device__ __forceinline__ void block_publish(double (*s_warp)[WARPS], double *partial, int n_sys) {
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int s = warp; s < n_sys; s += WARPS) {
-        double v = lane < WARPS ? s_warp[s][lane] : 0.0;
-        v = warp_sum(v);
-        if (lane == 0) partial[(long long)s * gridDim.x + blockIdx.x] = v;
-    }
+__device__ __forceinline__ void ll_store(ulonglong2 *p, double v, unsigned flag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long lo = ((unsigned long long)flag << 32) | (bits & 0xffffffffull);
+    const unsigned long long hi = ((unsigned long long)flag << 32) | (bits >> 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
 }
 
-// after a grid barrier: s_tot[s] = sum over blocks, same order in every CTA
-__device__ __forceinline__ void block_collect(const double *partial, double *s_tot, int n_sys) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int s = warp; s < n_sys; s += WARPS) {
-        const double *p = partial + (long long)s * gridDim.x;
-        double v = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(p + i);
+__device__ __forceinline__ double ll_wait(const ulonglong2 *p, unsigned flag) {
+    unsigned long long lo, hi;
+    do {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    } while ((unsigned)(lo >> 32) != flag || (unsigned)(hi >> 32) != flag);
+    return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+}
+
+// Barrier + all-reduce.  In: s_warp[s*MAXW + warp] partial of every warp of this CTA for every
+// system.  Out: s_tot[s] = sum over the whole grid, identical in every CTA.  All global writes
+// made by this CTA before the call are visible to every CTA after it.
+__device__ __forceinline__ void grid_allreduce(const CgArgs &a, double *s_warp, double *s_tot, unsigned &epoch) {
+    epoch++;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    ulonglong2 *slots = a.slots + (size_t)(epoch & 1u) * a.n_sys * gridDim.x;
+    __syncthreads();
+    for (int s = warp; s < a.n_sys; s += nwarps) {
+        double v = lane < nwarps ? s_warp[s * MAXW + lane] : 0.0;
         v = warp_sum(v);
-        if (lane == 0) s_tot[s] = v;
+        if (lane == 0) {
+            __threadfence();  // release: this CTA's vector writes (ordered by the barrier above) before the slot
+            ll_store(slots + (size_t)s * gridDim.x + blockIdx.x, v, epoch);
+        }
+        double t = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) t += ll_wait(slots + (size_t)s * gridDim.x + i, epoch);
+        t = warp_sum(t);
+        if (lane == 0) s_tot[s] = t;
+        __threadfence();  // acquire: other CTAs' writes before anything this CTA reads next
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_kernel(CgArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double s_warp[JF_MAX_SYS][WARPS];
-    __shared__ double s_tot[JF_MAX_SYS];
-    __shared__ double s_normb[JF_MAX_SYS], s_resid[JF_MAX_SYS], s_alpha[JF_MAX_SYS], s_beta[JF_MAX_SYS];
-    __shared__ int s_done[JF_MAX_SYS], s_iters[JF_MAX_SYS];
-    __shared__ int s_alldone;
+struct CgShared {
+    double warp[JF_MAX_SYS * MAXW];
+    double tot[JF_MAX_SYS];
+    double normb[JF_MAX_SYS], resid[JF_MAX_SYS], alpha[JF_MAX_SYS], beta[JF_MAX_SYS];
+    int done[JF_MAX_SYS], iters[JF_MAX_SYS];
+    int alldone;
+};
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // consecutive slices go to different CTAs first, so small systems spread over all SMs
-    const long long wg = (long long)warp * gridDim.x + blockIdx.x;
-    const long long nwg = (long long)gridDim.x * WARPS;
-    const long long vstride = a.Nf_pad * 4;
-    double *partA = a.partial;
-    double *partB = a.partial + (long long)a.n_sys * gridDim.x;
-
+__device__ __forceinline__ void cg_init_flags(const CgArgs &a, CgShared &sh) {
     if (threadIdx.x < a.n_sys) {
-        s_done[threadIdx.x] = a.state[threadIdx.x].active ? 0 : 1;
-        s_iters[threadIdx.x] = 0;
-        s_beta[threadIdx.x] = 0.0;
+        sh.done[threadIdx.x] = a.state[threadIdx.x].active ? 0 : 1;
+        sh.iters[threadIdx.x] = 0;
+        sh.beta[threadIdx.x] = 0.0;
+    }
+    for (int i = threadIdx.x; i < JF_MAX_SYS * MAXW; i += blockDim.x) sh.warp[i] = 0.0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cg_after_normb(const CgArgs &a, CgShared &sh) {
+    if (threadIdx.x < a.n_sys) {
+        const int s = threadIdx.x;
+        sh.normb[s] = sh.tot[s];
+        sh.resid[s] = sh.tot[s];
+        if (!sh.done[s] && sh.tot[s] == 0.0) sh.done[s] = 1;  // cg returns 0 when normb == 0
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ bool cg_all_done(const CgArgs &a, CgShared &sh) {
+    if (threadIdx.x == 0) {
+        int all = 1;
+        for (int s = 0; s < a.n_sys; s++) all &= sh.done[s];
+        sh.alldone = all;
+    }
+    __syncthreads();
+    return sh.alldone != 0;
+}
+
+__device__ __forceinline__ void cg_after_pAp(const CgArgs &a, CgShared &sh) {
+    if (threadIdx.x < a.n_sys && !sh.done[threadIdx.x]) sh.alpha[threadIdx.x] = sh.resid[threadIdx.x] / sh.tot[threadIdx.x];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cg_after_rr(const CgArgs &a, CgShared &sh, long long it) {
+    if (threadIdx.x < a.n_sys && !sh.done[threadIdx.x]) {
+        const int s = threadIdx.x;
+        const double rsnew = sh.tot[s];
+        sh.iters[s] = (int)it;
+        if (rsnew < a.tol * sh.normb[s] || it == a.maxiter) {
+            sh.done[s] = 1;
+        } else {
+            sh.beta[s] = rsnew / sh.resid[s];
+            sh.resid[s] = rsnew;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cg_write_state(const CgArgs &a, CgShared &sh) {
+    if (blockIdx.x == 0 && threadIdx.x < a.n_sys && a.state[threadIdx.x].active) {
+        const int s = threadIdx.x;
+        a.state[s].cg_iters = sh.iters[s];
+        a.state[s].normb = sh.normb[s];
+        a.state[s].resid = sh.resid[s];
+        if (a.apply_update) a.state[s].du = a.step * a.step * sh.tot[s];
+    }
+}
+
+// =================================================================================================
+// resident: one warp per (system, slice); matrix slice in shared memory, vectors in registers
+// =================================================================================================
+__global__ void __launch_bounds__(MAXW * 32, 1) jf_cg_resident_kernel(CgArgs a) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ CgShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)warp * gridDim.x + blockIdx.x;  // consecutive slices on different SMs
+    const bool have = item < (long long)a.n_sys * a.n_slices;
+    const int s = have ? (int)(item / a.n_slices) : 0;
+    const long long sl = have ? item - (long long)s * a.n_slices : 0;
+    const long long row = sl * 32 + lane;
+    const long long vstride = a.Nf_pad * 4;
+    const size_t per_warp = (size_t)a.wmax * (288 * sizeof(double) + 32 * sizeof(int));
+    double *mv = (double *)(dyn_smem + warp * per_warp);
+    int *mc = (int *)(mv + (size_t)a.wmax * 288);
+    unsigned epoch = 0;
+
+    cg_init_flags(a, sh);
+    const bool mine = have && !sh.done[s];
+
+    // stage the slice once: values in SELL order (lane-contiguous), column indices
+    int w = 0;
+    if (mine) {
+        const int q0 = a.slice_ptr[sl];
+        w = (a.slice_ptr[sl + 1] - q0) >> 5;
+        const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288;
+        for (int i = lane; i < w * 288; i += 32) mv[i] = v[i];
+        for (int j = 0; j < w; j++) mc[j * 32 + lane] = a.sell_col[q0 + j * 32 + lane];
+    }
+    __syncwarp();
+
+    double4 *R4 = (double4 *)(a.r + s * vstride);
+    double4 *P4[2] = {(double4 *)(a.p0 + s * vstride), (double4 *)(a.p1 + s * vstride)};
+    double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, y0 = 0, y1 = 0, y2 = 0;
+    double acc = 0.0;
+    if (mine) {
+        const double4 bv = ((const double4 *)(a.b + s * vstride))[row];
+        r0 = bv.x; r1 = bv.y; r2 = bv.z;
+        R4[row] = bv;
+        P4[1][row] = make_double4(0.0, 0.0, 0.0, 0.0);
+        acc = r0 * r0 + r1 * r1 + r2 * r2;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
+    grid_allreduce(a, sh.warp, sh.tot, epoch);
+    cg_after_normb(a, sh);
+
+    int cur = 0;
+    for (long long it = 1; it <= a.maxiter; it++) {
+        if (cg_all_done(a, sh)) break;
+        const bool act = have && !sh.done[s];
+        acc = 0.0;
+        if (act) {
+            const double beta = sh.beta[s];
+            const double4 *Rn = R4, *Po = P4[cur ^ 1];
+            y0 = y1 = y2 = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < w; j++) {
+                const int c = mc[j * 32 + lane];
+                const double4 rj = Rn[c], pj = Po[c];
+                const double px = fma(beta, pj.x, rj.x), py = fma(beta, pj.y, rj.y), pz = fma(beta, pj.z, rj.z);
+                const double *vj = mv + j * 288 + lane;
+                y0 = fma(vj[0], px, y0);
+                y0 = fma(vj[32], py, y0);
+                y0 = fma(vj[64], pz, y0);
+                y1 = fma(vj[96], px, y1);
+                y1 = fma(vj[128], py, y1);
+                y1 = fma(vj[160], pz, y1);
+                y2 = fma(vj[192], px, y2);
+                y2 = fma(vj[224], py, y2);
+                y2 = fma(vj[256], pz, y2);
+            }
+            p0 = fma(beta, p0, r0);
+            p1 = fma(beta, p1, r1);
+            p2 = fma(beta, p2, r2);
+            P4[cur][row] = make_double4(p0, p1, p2, 0.0);
+            acc = p0 * y0 + p1 * y1 + p2 * y2;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
+        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        cg_after_pAp(a, sh);
+
+        acc = 0.0;
+        if (act) {
+            const double alpha = sh.alpha[s];
+            x0 = fma(alpha, p0, x0);
+            x1 = fma(alpha, p1, x1);
+            x2 = fma(alpha, p2, x2);
+            r0 = fma(-alpha, y0, r0);
+            r1 = fma(-alpha, y1, r1);
+            r2 = fma(-alpha, y2, r2);
+            R4[row] = make_double4(r0, r1, r2, 0.0);
+            acc = r0 * r0 + r1 * r1 + r2 * r2;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
+        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        cg_after_rr(a, sh, it);
+        cur ^= 1;
+    }
+
+    // (A12) U[free] += step * x ; du = step^2 * sum x^2 ; x kept for jf_get_cg_solution
+    acc = 0.0;
+    if (have && a.state[s].active) {
+        ((double4 *)(a.x + s * vstride))[row] = make_double4(x0, x1, x2, 0.0);
+        if (a.apply_update && row < a.Nf) {
+            double *U = a.U + ((long long)s * a.N + row) * 3;
+            U[0] += a.step * x0;
+            U[1] += a.step * x1;
+            U[2] += a.step * x2;
+            acc = x0 * x0 + x1 * x1 + x2 * x2;
+        }
+    }
+    if (a.apply_update) {
+        acc = warp_sum(acc);
+        if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
+        grid_allreduce(a, sh.warp, sh.tot, epoch);
+    }
+    cg_write_state(a, sh);
+}
+
+// =================================================================================================
+// streaming: matrix from L2/HBM, vectors in global memory, warps loop over (system, slice) items
+// =================================================================================================
+__global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_stream_kernel(CgArgs a) {
+    __shared__ CgShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const long long wg = (long long)warp * gridDim.x + blockIdx.x;
+    const long long nwg = (long long)gridDim.x * nwarps;
+    const long long vstride = a.Nf_pad * 4;
+    unsigned epoch = 0;
+
+    cg_init_flags(a, sh);
 
     // ---- init: x = 0, r = b, pold = 0, normb = b.b --------------------------------------------
     for (int s = 0; s < a.n_sys; s++) {
         double acc = 0.0;
-        if (!s_done[s]) {
+        if (!sh.done[s]) {
             const double4 *b4 = (const double4 *)(a.b + s * vstride);
             double4 *x4 = (double4 *)(a.x + s * vstride), *r4 = (double4 *)(a.r + s * vstride), *q4 = (double4 *)(a.p1 + s * vstride);
             for (long long sl = wg; sl < a.n_slices; sl += nwg) {
@@ -112,36 +319,22 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_kernel(CgArgs a) {
             }
         }
         acc = warp_sum(acc);
-        if (lane == 0) s_warp[s][warp] = acc;
+        if (lane == 0) sh.warp[s * MAXW + warp] = acc;
     }
-    block_publish(s_warp, partA, a.n_sys);
-    grid.sync();
-    block_collect(partA, s_tot, a.n_sys);
-    if (threadIdx.x < a.n_sys) {
-        const int s = threadIdx.x;
-        s_normb[s] = s_tot[s];
-        s_resid[s] = s_tot[s];
-        if (!s_done[s] && s_tot[s] == 0.0) s_done[s] = 1;  // cg returns 0 when normb == 0
-    }
-    __syncthreads();
+    grid_allreduce(a, sh.warp, sh.tot, epoch);
+    cg_after_normb(a, sh);
 
     int cur = 0;  // phase A writes p into buffer `cur`, reads pold from the other one
     for (long long it = 1; it <= a.maxiter; it++) {
-        if (threadIdx.x == 0) {
-            int all = 1;
-            for (int s = 0; s < a.n_sys; s++) all &= s_done[s];
-            s_alldone = all;
-        }
-        __syncthreads();
-        if (s_alldone) break;
+        if (cg_all_done(a, sh)) break;
         double *pnew_base = cur ? a.p1 : a.p0;
         const double *pold_base = cur ? a.p0 : a.p1;
 
         // ---- phase A: Ap = K (r + beta pold), p.Ap ------------------------------------------------
         for (int s = 0; s < a.n_sys; s++) {
             double acc = 0.0;
-            if (!s_done[s]) {
-                const double beta = s_beta[s];
+            if (!sh.done[s]) {
+                const double beta = sh.beta[s];
                 const double4 *r4 = (const double4 *)(a.r + s * vstride);
                 const double4 *po4 = (const double4 *)(pold_base + s * vstride);
                 double4 *pn4 = (double4 *)(pnew_base + s * vstride);
@@ -178,19 +371,16 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_kernel(CgArgs a) {
                 }
             }
             acc = warp_sum(acc);
-            if (lane == 0) s_warp[s][warp] = acc;
+            if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         }
-        block_publish(s_warp, partA, a.n_sys);
-        grid.sync();
-        block_collect(partA, s_tot, a.n_sys);
-        if (threadIdx.x < a.n_sys && !s_done[threadIdx.x]) s_alpha[threadIdx.x] = s_resid[threadIdx.x] / s_tot[threadIdx.x];
-        __syncthreads();
+        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        cg_after_pAp(a, sh);
 
         // ---- phase B: x += alpha p, r -= alpha Ap, r.r ----------------------------------------------
         for (int s = 0; s < a.n_sys; s++) {
             double acc = 0.0;
-            if (!s_done[s]) {
-                const double alpha = s_alpha[s];
+            if (!sh.done[s]) {
+                const double alpha = sh.alpha[s];
                 double4 *x4 = (double4 *)(a.x + s * vstride), *r4 = (double4 *)(a.r + s * vstride);
                 const double4 *pn4 = (const double4 *)(pnew_base + s * vstride);
                 const double4 *Ap4 = (const double4 *)(a.Ap + s * vstride);
@@ -210,23 +400,10 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_kernel(CgArgs a) {
                 }
             }
             acc = warp_sum(acc);
-            if (lane == 0) s_warp[s][warp] = acc;
+            if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         }
-        block_publish(s_warp, partB, a.n_sys);
-        grid.sync();
-        block_collect(partB, s_tot, a.n_sys);
-        if (threadIdx.x < a.n_sys && !s_done[threadIdx.x]) {
-            const int s = threadIdx.x;
-            const double rsnew = s_tot[s];
-            s_iters[s] = (int)it;
-            if (rsnew < a.tol * s_normb[s] || it == a.maxiter) {
-                s_done[s] = 1;
-            } else {
-                s_beta[s] = rsnew / s_resid[s];
-                s_resid[s] = rsnew;
-            }
-        }
-        __syncthreads();
+        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        cg_after_rr(a, sh, it);
         cur ^= 1;
     }
 
@@ -249,32 +426,55 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_kernel(CgArgs a) {
                 }
             }
             acc = warp_sum(acc);
-            if (lane == 0) s_warp[s][warp] = acc;
+            if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         }
-        block_publish(s_warp, partA, a.n_sys);
-        grid.sync();
-        block_collect(partA, s_tot, a.n_sys);
+        grid_allreduce(a, sh.warp, sh.tot, epoch);
     }
-    if (blockIdx.x == 0 && threadIdx.x < a.n_sys && a.state[threadIdx.x].active) {
-        const int s = threadIdx.x;
-        a.state[s].cg_iters = s_iters[s];
-        a.state[s].normb = s_normb[s];
-        a.state[s].resid = s_resid[s];
-        if (a.apply_update) a.state[s].du = a.step * a.step * s_tot[s];
-    }
+    cg_write_state(a, sh);
 }
 
 }  // namespace
 
 int jf_cg_configure(jf_ctx *c) {
+    // widest slice
+    int wmax = 1;
+    for (int64_t k = 0; k < c->n_slices; k++) wmax = std::max(wmax, (c->h_slice_ptr[k + 1] - c->h_slice_ptr[k]) / JF_SLICE);
+    c->cg_wmax = wmax;
+    cudaFuncAttributes fa;
+    JF_CUDA(cudaFuncGetAttributes(&fa, jf_cg_resident_kernel));
+    int max_optin = 0;
+    JF_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const size_t per_warp = (size_t)wmax * (288 * sizeof(double) + 32 * sizeof(int));
+    long long avail = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024;
+    int warps = (int)std::min<long long>(MAXW, avail > 0 ? avail / (long long)per_warp : 0);
+    const long long items = (long long)c->n_sys * c->n_slices;
+    c->cg_resident = 0;
+    if (warps >= 1 && items <= (long long)warps * c->sm_count && !(c->flags & JF_FLAG_NO_RESIDENT)) {
+        // fewest warps per CTA that still cover all items with one CTA per SM
+        int need = (int)((items + c->sm_count - 1) / c->sm_count);
+        warps = std::max(1, std::min(warps, need));
+        size_t smem = per_warp * warps;
+        JF_CUDA(cudaFuncSetAttribute(jf_cg_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_resident_kernel, warps * 32, smem));
+        if (per_sm >= 1) {
+            c->cg_resident = 1;
+            c->cg_res_warps = warps;
+            c->cg_res_smem = smem;
+            c->cg_grid = (int)std::min<long long>(c->sm_count, (items + warps - 1) / warps);
+            if (c->cg_grid < 1) c->cg_grid = 1;
+            return 0;
+        }
+    }
     int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_kernel, JF_CG_BLOCK, 0));
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_stream_kernel, JF_CG_BLOCK, 0));
     if (per_sm < 1) {
         jf_set_error("CG kernel does not fit on an SM");
         return JF_ERR_CUDA;
     }
     // enough CTAs to give every slice of every system its own warp, at most what can be co-resident
-    long long want = (c->n_slices + WARPS - 1) / WARPS;
+    const int wpb = JF_CG_BLOCK / 32;
+    long long want = (items + wpb - 1) / wpb;
     long long cap = (long long)c->sm_count * per_sm;
     long long grid = want < c->sm_count ? c->sm_count : (want > cap ? cap : want);
     grid = (grid + c->sm_count - 1) / c->sm_count * c->sm_count;
@@ -294,7 +494,7 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.p0 = c->d_p0;
     a.p1 = c->d_p1;
     a.Ap = c->d_Ap;
-    a.partial = c->d_partial;
+    a.slots = (ulonglong2 *)c->d_partial;
     a.state = c->d_state;
     a.U = c->d_U;
     a.N = c->N;
@@ -303,12 +503,19 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.n_slices = c->n_slices;
     a.n_slots = c->n_slots;
     a.n_sys = c->n_sys;
+    a.wmax = c->cg_wmax;
     a.tol = tol;
     a.maxiter = maxiter;
     a.step = step;
     a.apply_update = apply_update;
+    // epochs restart at 1 in every launch: clear the flag words first (a few KB, same stream)
+    JF_CUDA(cudaMemsetAsync(c->d_partial, 0, (size_t)2 * c->n_sys * c->cg_grid * sizeof(ulonglong2), c->stream));
     void *args[] = {&a};
-    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_kernel, dim3(c->cg_grid), dim3(JF_CG_BLOCK), args, 0, c->stream));
+    if (c->cg_resident)
+        JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_resident_kernel, dim3(c->cg_grid), dim3(c->cg_res_warps * 32), args,
+                                            c->cg_res_smem, c->stream));
+    else
+        JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_stream_kernel, dim3(c->cg_grid), dim3(JF_CG_BLOCK), args, 0, c->stream));
     c->stats.kernel_launches++;
     c->stats.cg_launches++;
     return 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -86,6 +87,8 @@ struct jf_ctx {
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
     unsigned int *d_barrier = nullptr; // grid barrier words
     int cg_grid = 0, elem_grid = 0;
+    int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0;
+    size_t cg_res_smem = 0;
 
     bool have_material = false, evaluated = false;
     std::vector<char> have_targets;

@@ -221,3 +221,21 @@ def test_golden_oracle_solutions(name, beams):
     assert np.array_equal(np.isnan(curve), ~ok)
     assert np.max(np.abs(curve[ok] / g["curve"][ok] - 1)) < 1e-3
     assert np.allclose(out["relrec"][:, 1], g["relrec"][:, 1], rtol=1e-4)
+
+
+def test_resident_and_streaming_cg_agree(beams):
+    """Same arithmetic, different data placement (shared-memory/register resident vs streamed):
+    the two CG kernels must follow the same trajectory."""
+    from jointforces_b200 import _lib
+    c = make_case(0.4, 100.0)
+    res = []
+    for flags in (0, _lib.JF_FLAG_NO_RESIDENT):
+        with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams, flags=flags) as ctx:
+            ctx.set_material(*COLLAGEN12)
+            ctx.set_targets(c["f_target"])
+            ctx.set_displacements(np.zeros_like(c["coords"]))
+            relrec, cgit, n = ctx.relax(0.0033, 25, 0.01)
+            res.append((ctx.displacements(), cgit[0], ctx.info()["cg_resident"]))
+    assert res[0][2] == 1 and res[1][2] == 0
+    assert np.abs(res[0][1].astype(int) - res[1][1]).max() <= 2
+    assert np.linalg.norm(res[0][0] - res[1][0]) / np.linalg.norm(res[1][0]) < 2e-5
