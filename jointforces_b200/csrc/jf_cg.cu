@@ -10,11 +10,11 @@
 //            buffer), fused p.Ap partials
 //   phase B  x += alpha p, r -= alpha Ap, fused r.r partials
 //
-// Grid synchronisation and the dot products are ONE primitive (grid_allreduce): every CTA
-// publishes its partial sums in flag-carrying 16-byte slots (each 8-byte half holds 32 data bits
-// and the 32-bit epoch, so a half-written slot can never be mistaken for data), every CTA polls
-// all slots and adds them in the same fixed order.  That is a barrier and an all-reduce in one
-// L2 round trip, and results are bitwise reproducible for a given grid -- no atomics anywhere.
+// Dot products: lane -> warp shuffle tree -> one slot per CTA -> grid barrier -> every CTA adds
+// the slots in the same fixed order.  No atomics on data, so results are bitwise reproducible
+// for a given grid.  (A flag-in-data slot protocol that fuses barrier and reduction was measured
+// slower than the cooperative-groups barrier on 134-148 CTAs -- tools/micro/barrier_bench.cu,
+// DESIGN.md "Barrier" -- because every CTA polls every slot.)
 //
 // Two kernels share that skeleton:
 //   jf_cg_resident_kernel  every (system, 32-row slice) has its own warp for the whole solve: the
@@ -25,6 +25,9 @@
 //                          of blocks spread over the 148 SMs' shared memory).
 //   jf_cg_stream_kernel    larger meshes / wider batches: matrix streamed from L2/HBM in SELL-32
 //                          order (every warp load is a 256-byte line), vectors in global memory.
+// In both, the gathers of one batch of block columns are issued before any of them is consumed
+// (explicit register staging), because a row's 15-17 dependent L2 round trips were what bounded
+// the first version.
 //
 // Matrix: SELL-32 3x3 blocks (jf_assembly.cu); one thread owns one block row.  Vectors are
 // (row,4) doubles so a gathered node is one 32-byte sector.
@@ -32,9 +35,21 @@
 
 #include "jf_internal.h"
 
+namespace cg = cooperative_groups;
+
+#ifdef JF_CG_TIMING
+#include <cstdio>
+#define TMARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } } while (0)
+#else
+#define TMARK(i) do { } while (0)
+#endif
+
 namespace {
 
-constexpr int MAXW = 32;  // warps per CTA upper bound
+constexpr int MAXW = 32;      // warps per CTA upper bound (shared partial table stride)
+constexpr int RES_WARPS = 8;  // resident kernel: at most 8 warps per CTA -> 255 registers per thread
+constexpr int RES_BATCH = 9;  // block columns gathered per batch (resident)
+constexpr int STR_BATCH = 3;  // block columns gathered per batch (streaming)
 
 struct CgArgs {
     const int32_t *slice_ptr;
@@ -42,7 +57,7 @@ struct CgArgs {
     const double *val;
     const double *b;
     double *x, *r, *p0, *p1, *Ap;
-    ulonglong2 *slots;  // (2, n_sys, grid) flag-carrying partial sums
+    double *partial;  // (2, n_sys, grid) per-CTA partial sums, double-buffered by barrier parity
     jf_sys_state *state;
     double *U;
     long long N, Nf, Nf_pad, n_slices, n_slots;
@@ -54,47 +69,41 @@ struct CgArgs {
     int apply_update;
 };
 
+// one 32-byte vector entry with a single 256-bit load (LDG.E.256 on sm_100a): a gathered node costs
+// one L1tex wavefront per distinct line instead of two
+__device__ __forceinline__ double4 ld_node(const double4 *p) {
+    double4 v;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
 }
 
-__device__ __forceinline__ void ll_store(ulonglong2 *p, double v, unsigned flag) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    const unsigned long long lo = ((unsigned long long)flag << 32) | (bits & 0xffffffffull);
-    const unsigned long long hi = ((unsigned long long)flag << 32) | (bits >> 32);
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
-}
-
-__device__ __forceinline__ double ll_wait(const ulonglong2 *p, unsigned flag) {
-    unsigned long long lo, hi;
-    do {
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
-    } while ((unsigned)(lo >> 32) != flag || (unsigned)(hi >> 32) != flag);
-    return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
-}
-
 // Barrier + all-reduce.  In: s_warp[s*MAXW + warp] partial of every warp of this CTA for every
 // system.  Out: s_tot[s] = sum over the whole grid, identical in every CTA.  All global writes
-// made by this CTA before the call are visible to every CTA after it.
-__device__ __forceinline__ void grid_allreduce(const CgArgs &a, double *s_warp, double *s_tot, unsigned &epoch) {
+// made by this CTA before the call are visible to every CTA after it (grid.sync semantics).
+__device__ __forceinline__ void grid_allreduce(const CgArgs &a, cg::grid_group &grid, double *s_warp, double *s_tot,
+                                               unsigned &epoch) {
     epoch++;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    ulonglong2 *slots = a.slots + (size_t)(epoch & 1u) * a.n_sys * gridDim.x;
+    double *part = a.partial + (size_t)(epoch & 1u) * a.n_sys * gridDim.x;
     __syncthreads();
     for (int s = warp; s < a.n_sys; s += nwarps) {
         double v = lane < nwarps ? s_warp[s * MAXW + lane] : 0.0;
         v = warp_sum(v);
-        if (lane == 0) {
-            __threadfence();  // release: this CTA's vector writes (ordered by the barrier above) before the slot
-            ll_store(slots + (size_t)s * gridDim.x + blockIdx.x, v, epoch);
-        }
+        if (lane == 0) part[(size_t)s * gridDim.x + blockIdx.x] = v;
+    }
+    grid.sync();
+    for (int s = warp; s < a.n_sys; s += nwarps) {
+        const double *p = part + (size_t)s * gridDim.x;
         double t = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) t += ll_wait(slots + (size_t)s * gridDim.x + i, epoch);
+        for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(p + i);
         t = warp_sum(t);
         if (lane == 0) s_tot[s] = t;
-        __threadfence();  // acquire: other CTAs' writes before anything this CTA reads next
     }
     __syncthreads();
 }
@@ -124,17 +133,12 @@ __device__ __forceinline__ void cg_after_normb(const CgArgs &a, CgShared &sh) {
         sh.resid[s] = sh.tot[s];
         if (!sh.done[s] && sh.tot[s] == 0.0) sh.done[s] = 1;  // cg returns 0 when normb == 0
     }
-    __syncthreads();
-}
-
-__device__ __forceinline__ bool cg_all_done(const CgArgs &a, CgShared &sh) {
     if (threadIdx.x == 0) {
         int all = 1;
-        for (int s = 0; s < a.n_sys; s++) all &= sh.done[s];
+        for (int s = 0; s < a.n_sys; s++) all &= (sh.done[s] || sh.tot[s] == 0.0);
         sh.alldone = all;
     }
     __syncthreads();
-    return sh.alldone != 0;
 }
 
 __device__ __forceinline__ void cg_after_pAp(const CgArgs &a, CgShared &sh) {
@@ -142,17 +146,24 @@ __device__ __forceinline__ void cg_after_pAp(const CgArgs &a, CgShared &sh) {
     __syncthreads();
 }
 
+// convergence test, beta, and the all-done flag for the next iteration (one barrier for all three)
 __device__ __forceinline__ void cg_after_rr(const CgArgs &a, CgShared &sh, long long it) {
-    if (threadIdx.x < a.n_sys && !sh.done[threadIdx.x]) {
-        const int s = threadIdx.x;
-        const double rsnew = sh.tot[s];
-        sh.iters[s] = (int)it;
-        if (rsnew < a.tol * sh.normb[s] || it == a.maxiter) {
-            sh.done[s] = 1;
-        } else {
-            sh.beta[s] = rsnew / sh.resid[s];
-            sh.resid[s] = rsnew;
+    if (threadIdx.x == 0) {
+        int all = 1;
+        for (int s = 0; s < a.n_sys; s++) {
+            if (!sh.done[s]) {
+                const double rsnew = sh.tot[s];
+                sh.iters[s] = (int)it;
+                if (rsnew < a.tol * sh.normb[s] || it == a.maxiter) {
+                    sh.done[s] = 1;
+                } else {
+                    sh.beta[s] = rsnew / sh.resid[s];
+                    sh.resid[s] = rsnew;
+                }
+            }
+            all &= sh.done[s];
         }
+        sh.alldone = all;
     }
     __syncthreads();
 }
@@ -167,10 +178,22 @@ __device__ __forceinline__ void cg_write_state(const CgArgs &a, CgShared &sh) {
     }
 }
 
+#define JF_BLOCK_FMA(vj, STRIDE, px, py, pz)  \
+    y0 = fma((vj)[0 * (STRIDE)], px, y0);     \
+    y0 = fma((vj)[1 * (STRIDE)], py, y0);     \
+    y0 = fma((vj)[2 * (STRIDE)], pz, y0);     \
+    y1 = fma((vj)[3 * (STRIDE)], px, y1);     \
+    y1 = fma((vj)[4 * (STRIDE)], py, y1);     \
+    y1 = fma((vj)[5 * (STRIDE)], pz, y1);     \
+    y2 = fma((vj)[6 * (STRIDE)], px, y2);     \
+    y2 = fma((vj)[7 * (STRIDE)], py, y2);     \
+    y2 = fma((vj)[8 * (STRIDE)], pz, y2);
+
 // =================================================================================================
 // resident: one warp per (system, slice); matrix slice in shared memory, vectors in registers
 // =================================================================================================
-__global__ void __launch_bounds__(MAXW * 32, 1) jf_cg_resident_kernel(CgArgs a) {
+__global__ void __launch_bounds__(RES_WARPS * 32, 1) jf_cg_resident_kernel(CgArgs a) {
+    cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ CgShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,56 +222,68 @@ __global__ void __launch_bounds__(MAXW * 32, 1) jf_cg_resident_kernel(CgArgs a) 
     }
     __syncwarp();
 
-    double4 *R4 = (double4 *)(a.r + s * vstride);
-    double4 *P4[2] = {(double4 *)(a.p0 + s * vstride), (double4 *)(a.p1 + s * vstride)};
+    double4 *const R4 = (double4 *)(a.r + s * vstride);
+    double4 *const Pa = (double4 *)(a.p0 + s * vstride);
+    double4 *const Pb = (double4 *)(a.p1 + s * vstride);
     double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, y0 = 0, y1 = 0, y2 = 0;
     double acc = 0.0;
     if (mine) {
         const double4 bv = ((const double4 *)(a.b + s * vstride))[row];
         r0 = bv.x; r1 = bv.y; r2 = bv.z;
         R4[row] = bv;
-        P4[1][row] = make_double4(0.0, 0.0, 0.0, 0.0);
+        Pb[row] = make_double4(0.0, 0.0, 0.0, 0.0);
         acc = r0 * r0 + r1 * r1 + r2 * r2;
     }
     acc = warp_sum(acc);
     if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
-    grid_allreduce(a, sh.warp, sh.tot, epoch);
+    grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
     cg_after_normb(a, sh);
 
     int cur = 0;
+#ifdef JF_CG_TIMING
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
     for (long long it = 1; it <= a.maxiter; it++) {
-        if (cg_all_done(a, sh)) break;
+        if (sh.alldone) break;
+        TMARK(0);
         const bool act = have && !sh.done[s];
         acc = 0.0;
         if (act) {
             const double beta = sh.beta[s];
-            const double4 *Rn = R4, *Po = P4[cur ^ 1];
+            const double4 *Po = cur ? Pa : Pb;
+            double4 *Pn = cur ? Pb : Pa;
             y0 = y1 = y2 = 0.0;
-#pragma unroll 4
-            for (int j = 0; j < w; j++) {
-                const int c = mc[j * 32 + lane];
-                const double4 rj = Rn[c], pj = Po[c];
-                const double px = fma(beta, pj.x, rj.x), py = fma(beta, pj.y, rj.y), pz = fma(beta, pj.z, rj.z);
-                const double *vj = mv + j * 288 + lane;
-                y0 = fma(vj[0], px, y0);
-                y0 = fma(vj[32], py, y0);
-                y0 = fma(vj[64], pz, y0);
-                y1 = fma(vj[96], px, y1);
-                y1 = fma(vj[128], py, y1);
-                y1 = fma(vj[160], pz, y1);
-                y2 = fma(vj[192], px, y2);
-                y2 = fma(vj[224], py, y2);
-                y2 = fma(vj[256], pz, y2);
+            for (int j0 = 0; j0 < w; j0 += RES_BATCH) {
+                double4 rj[RES_BATCH], pj[RES_BATCH];
+#pragma unroll
+                int c[RES_BATCH];
+#pragma unroll
+                for (int k = 0; k < RES_BATCH; k++) c[k] = (j0 + k < w) ? mc[(j0 + k) * 32 + lane] : (int)row;
+#pragma unroll
+                for (int k = 0; k < RES_BATCH; k++) {
+                    rj[k] = ld_node(R4 + c[k]);
+                    pj[k] = ld_node(Po + c[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < RES_BATCH; k++) {
+                    if (j0 + k < w) {
+                        const double px = fma(beta, pj[k].x, rj[k].x), py = fma(beta, pj[k].y, rj[k].y), pz = fma(beta, pj[k].z, rj[k].z);
+                        const double *vj = mv + (j0 + k) * 288 + lane;
+                        JF_BLOCK_FMA(vj, 32, px, py, pz)
+                    }
+                }
             }
             p0 = fma(beta, p0, r0);
             p1 = fma(beta, p1, r1);
             p2 = fma(beta, p2, r2);
-            P4[cur][row] = make_double4(p0, p1, p2, 0.0);
+            Pn[row] = make_double4(p0, p1, p2, 0.0);
             acc = p0 * y0 + p1 * y1 + p2 * y2;
         }
         acc = warp_sum(acc);
         if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
-        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        TMARK(1);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+        TMARK(2);
         cg_after_pAp(a, sh);
 
         acc = 0.0;
@@ -265,10 +300,19 @@ __global__ void __launch_bounds__(MAXW * 32, 1) jf_cg_resident_kernel(CgArgs a) 
         }
         acc = warp_sum(acc);
         if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
-        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        TMARK(3);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+        TMARK(4);
         cg_after_rr(a, sh, it);
         cur ^= 1;
+        TMARK(5);
     }
+#ifdef JF_CG_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("cg-res iters %d cycles/iter: top %.0f phaseA %.0f arA %.0f phaseB %.0f arB %.0f tail %.0f\n", sh.iters[0],
+               (double)tacc[0] / sh.iters[0], (double)tacc[1] / sh.iters[0], (double)tacc[2] / sh.iters[0],
+               (double)tacc[3] / sh.iters[0], (double)tacc[4] / sh.iters[0], (double)tacc[5] / sh.iters[0]);
+#endif
 
     // (A12) U[free] += step * x ; du = step^2 * sum x^2 ; x kept for jf_get_cg_solution
     acc = 0.0;
@@ -285,7 +329,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) jf_cg_resident_kernel(CgArgs a) 
     if (a.apply_update) {
         acc = warp_sum(acc);
         if (lane == 0 && have) sh.warp[s * MAXW + warp] = acc;
-        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
     }
     cg_write_state(a, sh);
 }
@@ -293,7 +337,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) jf_cg_resident_kernel(CgArgs a) 
 // =================================================================================================
 // streaming: matrix from L2/HBM, vectors in global memory, warps loop over (system, slice) items
 // =================================================================================================
-__global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_stream_kernel(CgArgs a) {
+__global__ void __launch_bounds__(JF_CG_BLOCK, 1) jf_cg_stream_kernel(CgArgs a) {
+    cg::grid_group grid = cg::this_grid();
     __shared__ CgShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const long long wg = (long long)warp * gridDim.x + blockIdx.x;
@@ -321,12 +366,12 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_stream_kernel(CgArgs a) {
         acc = warp_sum(acc);
         if (lane == 0) sh.warp[s * MAXW + warp] = acc;
     }
-    grid_allreduce(a, sh.warp, sh.tot, epoch);
+    grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
     cg_after_normb(a, sh);
 
     int cur = 0;  // phase A writes p into buffer `cur`, reads pold from the other one
     for (long long it = 1; it <= a.maxiter; it++) {
-        if (cg_all_done(a, sh)) break;
+        if (sh.alldone) break;
         double *pnew_base = cur ? a.p1 : a.p0;
         const double *pold_base = cur ? a.p0 : a.p1;
 
@@ -346,24 +391,30 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_stream_kernel(CgArgs a) {
                     const int w = (a.slice_ptr[sl + 1] - q0) >> 5;
                     const double *v = vals + (long long)(q0 >> 5) * 288 + lane;
                     const int32_t *ci = a.sell_col + q0 + lane;
-                    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-#pragma unroll 4
-                    for (int j = 0; j < w; j++) {
-                        const int c = ci[32 * j];
-                        const double4 rj = r4[c], pj = po4[c];
-                        const double px = fma(beta, pj.x, rj.x), py = fma(beta, pj.y, rj.y), pz = fma(beta, pj.z, rj.z);
-                        const double *vj = v + 288 * j;
-                        y0 = fma(vj[0], px, y0);
-                        y0 = fma(vj[32], py, y0);
-                        y0 = fma(vj[64], pz, y0);
-                        y1 = fma(vj[96], px, y1);
-                        y1 = fma(vj[128], py, y1);
-                        y1 = fma(vj[160], pz, y1);
-                        y2 = fma(vj[192], px, y2);
-                        y2 = fma(vj[224], py, y2);
-                        y2 = fma(vj[256], pz, y2);
-                    }
                     const double4 ri = r4[row], pi = po4[row];
+                    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                    for (int j0 = 0; j0 < w; j0 += STR_BATCH) {
+                        int c[STR_BATCH];
+                        double4 rj[STR_BATCH], pj[STR_BATCH];
+                        double m[STR_BATCH][9];
+#pragma unroll
+                        for (int k = 0; k < STR_BATCH; k++) c[k] = (j0 + k < w) ? ci[32 * (j0 + k)] : (int)row;
+#pragma unroll
+                        for (int k = 0; k < STR_BATCH; k++) {
+                            const int jj = (j0 + k < w) ? j0 + k : j0;  // clamped: never read past the slice
+#pragma unroll
+                            for (int q = 0; q < 9; q++) m[k][q] = v[288 * jj + 32 * q];
+                            rj[k] = ld_node(r4 + c[k]);
+                            pj[k] = ld_node(po4 + c[k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < STR_BATCH; k++) {
+                            if (j0 + k < w) {
+                                const double px = fma(beta, pj[k].x, rj[k].x), py = fma(beta, pj[k].y, rj[k].y), pz = fma(beta, pj[k].z, rj[k].z);
+                                JF_BLOCK_FMA(m[k], 1, px, py, pz)
+                            }
+                        }
+                    }
                     const double px = fma(beta, pi.x, ri.x), py = fma(beta, pi.y, ri.y), pz = fma(beta, pi.z, ri.z);
                     pn4[row] = make_double4(px, py, pz, 0.0);
                     Ap4[row] = make_double4(y0, y1, y2, 0.0);
@@ -373,7 +424,7 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_stream_kernel(CgArgs a) {
             acc = warp_sum(acc);
             if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         }
-        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
         cg_after_pAp(a, sh);
 
         // ---- phase B: x += alpha p, r -= alpha Ap, r.r ----------------------------------------------
@@ -402,7 +453,7 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_stream_kernel(CgArgs a) {
             acc = warp_sum(acc);
             if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         }
-        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
         cg_after_rr(a, sh, it);
         cur ^= 1;
     }
@@ -428,7 +479,7 @@ __global__ void __launch_bounds__(JF_CG_BLOCK) jf_cg_stream_kernel(CgArgs a) {
             acc = warp_sum(acc);
             if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         }
-        grid_allreduce(a, sh.warp, sh.tot, epoch);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
     }
     cg_write_state(a, sh);
 }
@@ -446,7 +497,7 @@ int jf_cg_configure(jf_ctx *c) {
     JF_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     const size_t per_warp = (size_t)wmax * (288 * sizeof(double) + 32 * sizeof(int));
     long long avail = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024;
-    int warps = (int)std::min<long long>(MAXW, avail > 0 ? avail / (long long)per_warp : 0);
+    int warps = (int)std::min<long long>(RES_WARPS, avail > 0 ? avail / (long long)per_warp : 0);
     const long long items = (long long)c->n_sys * c->n_slices;
     c->cg_resident = 0;
     if (warps >= 1 && items <= (long long)warps * c->sm_count && !(c->flags & JF_FLAG_NO_RESIDENT)) {
@@ -494,7 +545,7 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.p0 = c->d_p0;
     a.p1 = c->d_p1;
     a.Ap = c->d_Ap;
-    a.slots = (ulonglong2 *)c->d_partial;
+    a.partial = c->d_partial;
     a.state = c->d_state;
     a.U = c->d_U;
     a.N = c->N;
@@ -508,8 +559,6 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.maxiter = maxiter;
     a.step = step;
     a.apply_update = apply_update;
-    // epochs restart at 1 in every launch: clear the flag words first (a few KB, same stream)
-    JF_CUDA(cudaMemsetAsync(c->d_partial, 0, (size_t)2 * c->n_sys * c->cg_grid * sizeof(ulonglong2), c->stream));
     void *args[] = {&a};
     if (c->cg_resident)
         JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_resident_kernel, dim3(c->cg_grid), dim3(c->cg_res_warps * 32), args,

@@ -131,34 +131,72 @@ static void build_adjacency(int64_t N, int64_t T, const int32_t *tets, std::vect
     for (int64_t i = 0; i < N; i++) std::copy(raw.begin() + cnt[i], raw.begin() + cnt[i] + (ptr[i + 1] - ptr[i]), adj.begin() + ptr[i]);
 }
 
-// Cuthill-McKee over the free nodes, then degree-sort inside windows so SELL slices pad little
+// Cost of the SpMV's vector gathers for a candidate ordering of the free nodes: the number of
+// distinct 128-byte lines touched by each 32-lane gather (one per slice and block column), summed.
+// On B200 that is what bounds the CG kernel for these matrices (L1tex wavefronts; DESIGN.md
+// "CG"), so the ordering is chosen by it rather than by bandwidth alone.  Also returns the padded
+// slot count.
+static double gather_cost(const std::vector<int32_t> &order, int64_t N, const std::vector<int64_t> &ptr,
+                          const std::vector<int32_t> &adj, int64_t *slots_out) {
+    const int64_t nf = (int64_t)order.size();
+    std::vector<int32_t> o2n(N, -1);
+    for (int64_t i = 0; i < nf; i++) o2n[order[i]] = (int32_t)i;
+    std::vector<int32_t> cols[JF_SLICE];
+    int32_t tmp[JF_SLICE];
+    double lines = 0;
+    int64_t slots = 0;
+    for (int64_t s0 = 0; s0 < nf; s0 += JF_SLICE) {
+        size_t w = 0;
+        const int nrow = (int)std::min<int64_t>(JF_SLICE, nf - s0);
+        for (int r = 0; r < nrow; r++) {
+            cols[r].clear();
+            const int32_t old = order[s0 + r];
+            for (int64_t k = ptr[old]; k < ptr[old + 1]; k++)
+                if (o2n[adj[k]] >= 0) cols[r].push_back(o2n[adj[k]]);
+            std::sort(cols[r].begin(), cols[r].end());
+            w = std::max(w, cols[r].size());
+        }
+        slots += (int64_t)w * JF_SLICE;
+        for (size_t j = 0; j < w; j++) {
+            int n = 0;
+            for (int r = 0; r < nrow; r++)
+                if (j < cols[r].size()) tmp[n++] = cols[r][j] >> 2;  // four 32-byte entries per line
+            std::sort(tmp, tmp + n);
+            lines += (double)(std::unique(tmp, tmp + n) - tmp);
+        }
+    }
+    if (slots_out) *slots_out = slots;
+    return lines;
+}
+
+// Candidate orderings of the free nodes: the caller's order, and Cuthill-McKee (breadth-first,
+// neighbours by increasing degree); the one with the cheapest gathers wins.
 static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int64_t> &ptr,
                         const std::vector<int32_t> &adj) {
     int64_t N = c->N;
     std::vector<int32_t> order;
     order.reserve(N);
-    if (c->flags & JF_FLAG_NO_REORDER) {
-        for (int64_t i = 0; i < N; i++)
-            if (movable[i]) order.push_back((int32_t)i);
-    } else {
+    for (int64_t i = 0; i < N; i++)
+        if (movable[i]) order.push_back((int32_t)i);
+    if (!(c->flags & JF_FLAG_NO_REORDER)) {
+        std::vector<int32_t> cm;
+        cm.reserve(order.size());
         std::vector<int32_t> deg(N, 0);
         for (int64_t i = 0; i < N; i++)
             if (movable[i])
                 for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) deg[i] += movable[adj[k]] ? 1 : 0;
         std::vector<char> seen(N, 0);
         // seeds in order of increasing degree (first unvisited wins)
-        std::vector<int32_t> seeds;
-        for (int64_t i = 0; i < N; i++)
-            if (movable[i]) seeds.push_back((int32_t)i);
+        std::vector<int32_t> seeds(order);
         std::stable_sort(seeds.begin(), seeds.end(), [&](int32_t a, int32_t b) { return deg[a] < deg[b]; });
         std::vector<int32_t> nb;
         for (int32_t seed : seeds) {
             if (seen[seed]) continue;
             seen[seed] = 1;
-            size_t head = order.size();
-            order.push_back(seed);
-            while (head < order.size()) {
-                int32_t u = order[head++];
+            size_t head = cm.size();
+            cm.push_back(seed);
+            while (head < cm.size()) {
+                int32_t u = cm[head++];
                 nb.clear();
                 for (int64_t k = ptr[u]; k < ptr[u + 1]; k++) {
                     int32_t v = adj[k];
@@ -168,14 +206,14 @@ static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int
                     }
                 }
                 std::stable_sort(nb.begin(), nb.end(), [&](int32_t a, int32_t b) { return deg[a] < deg[b]; });
-                order.insert(order.end(), nb.begin(), nb.end());
+                cm.insert(cm.end(), nb.begin(), nb.end());
             }
         }
-        const size_t window = 1024;
-        for (size_t a = 0; a < order.size(); a += window) {
-            size_t b = std::min(order.size(), a + window);
-            std::stable_sort(order.begin() + a, order.begin() + b, [&](int32_t x, int32_t y) { return deg[x] > deg[y]; });
-        }
+        int64_t slots_id = 0, slots_cm = 0;
+        const double cost_id = gather_cost(order, N, ptr, adj, &slots_id);
+        const double cost_cm = gather_cost(cm, N, ptr, adj, &slots_cm);
+        // a gathered line and ~2 padded block slots cost about the same L1tex time
+        if (cost_cm + 0.5 * (double)slots_cm / JF_SLICE < cost_id + 0.5 * (double)slots_id / JF_SLICE) order.swap(cm);
     }
     c->Nf = (int64_t)order.size();
     for (int64_t i = 0; i < N; i++)
