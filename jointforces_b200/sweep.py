@@ -106,7 +106,8 @@ def run_sweep(meshfile, outfolder, values, material, var_arg='pressure', max_ite
     curves = np.full((len(mine), n_bins), np.nan)
     mat_par = SemiAffineFiberMaterial(material['K_0'], material['D_0'], material['L_S'], material['D_S']).serialize()
     for j, (i, bc, res) in enumerate(zip(mine, bcs, results)):
-        curves[j] = sim.radial_median_curve(coords, res['U'], r_in, x)
+        # the radius exactly as the table builder recovers it from parameters.txt (simulation.py:296-297)
+        curves[j] = sim.radial_median_curve(coords, res['U'], (r_in * 1e6) * 10 ** -6, x)
         if write:
             folder = outfolder + '/simulation' + str(int(i)).zfill(6)
             os.makedirs(folder, exist_ok=True)

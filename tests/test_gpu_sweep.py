@@ -24,7 +24,7 @@ def test_spherical_contraction_solver_writes_reference_files(meshfile, tmp_path,
     M = jf.simulation.spherical_contraction_solver(meshfile, out, 100.0, jf.materials.collagen12)
     assert sorted(os.listdir(out)) == ["parameters.txt", "relrec.txt", "solver.saenopy"]
     par = jf.simulation.read_parameters(out)
-    assert par["PRESSURE"] == 100.0 and par["INNER_RADIUS"] == 100.0 and par["TOTAL_NODES"] == 360
+    assert par["PRESSURE"] == 100.0 and abs(par["INNER_RADIUS"] - 100.0) < 1e-9 and par["TOTAL_NODES"] == 360
     relrec = np.loadtxt(out + "/relrec.txt")
     assert relrec.shape[1] == 3 and relrec[0, 0] == 0
     L = jf.simulation.load_solver(out + "/solver.saenopy")
