@@ -1,0 +1,163 @@
+// Shared pieces of the CG kernels (jf_cg_resident.cu, jf_cg_stream.cu): arguments, the barrier +
+// all-reduce primitive, the per-system scalar state machine of Hestenes-Stiefel CG.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "jf_internal.h"
+
+namespace cg = cooperative_groups;
+
+#ifdef JF_CG_TIMING
+#include <cstdio>
+#define TMARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } } while (0)
+#else
+#define TMARK(i) do { } while (0)
+#endif
+
+constexpr int MAXW = 32;      // warps per CTA upper bound (shared partial table stride)
+constexpr int RES_WARPS = 8;  // resident kernel: at most 8 warps per CTA -> 255 registers per thread
+constexpr int STR_BATCH = 3;  // block columns gathered per batch (streaming)
+
+struct CgArgs {
+    const int32_t *slice_ptr;
+    const int32_t *sell_col;
+    const double *val;
+    const double *b;
+    double *x, *r, *p0, *p1, *Ap;
+    double *partial;  // (2, n_sys, grid) per-CTA partial sums, double-buffered by barrier parity
+    jf_sys_state *state;
+    double *U;
+    long long N, Nf, Nf_pad, n_slices, n_slots;
+    int n_sys;
+    int wmax;  // widest slice (resident kernel: shared-memory stride)
+    // resident kernel only: per-CTA halo (sorted unique block columns its slices touch)
+    const int32_t *halo_ptr;    // (ctas_per_sys + 1)
+    const int32_t *halo_nodes;  // concatenated halo lists
+    const uint16_t *lcol;       // (n_slots) block column as index into the owning CTA's halo list
+    int hmax, ctas_per_sys;
+    double tol;
+    long long maxiter;
+    double step;
+    int apply_update;
+};
+
+// one 32-byte vector entry with a single 256-bit load (LDG.E.256 on sm_100a): a gathered node costs
+// one L1tex wavefront per distinct line instead of two
+__device__ __forceinline__ double4 ld_node(const double4 *p) {
+    double4 v;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Barrier + all-reduce.  In: s_warp[s*MAXW + warp] partial of every warp of this CTA for every
+// system.  Out: s_tot[s] = sum over the whole grid, identical in every CTA.  All global writes
+// made by this CTA before the call are visible to every CTA after it (grid.sync semantics).
+__device__ __forceinline__ void grid_allreduce(const CgArgs &a, cg::grid_group &grid, double *s_warp, double *s_tot,
+                                               unsigned &epoch) {
+    epoch++;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double *part = a.partial + (size_t)(epoch & 1u) * a.n_sys * gridDim.x;
+    __syncthreads();
+    for (int s = warp; s < a.n_sys; s += nwarps) {
+        double v = lane < nwarps ? s_warp[s * MAXW + lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) part[(size_t)s * gridDim.x + blockIdx.x] = v;
+    }
+    grid.sync();
+    for (int s = warp; s < a.n_sys; s += nwarps) {
+        const double *p = part + (size_t)s * gridDim.x;
+        double t = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(p + i);
+        t = warp_sum(t);
+        if (lane == 0) s_tot[s] = t;
+    }
+    __syncthreads();
+}
+
+struct CgShared {
+    double warp[JF_MAX_SYS * MAXW];
+    double tot[JF_MAX_SYS];
+    double normb[JF_MAX_SYS], resid[JF_MAX_SYS], alpha[JF_MAX_SYS], beta[JF_MAX_SYS];
+    int done[JF_MAX_SYS], iters[JF_MAX_SYS];
+    int alldone;
+};
+
+__device__ __forceinline__ void cg_init_flags(const CgArgs &a, CgShared &sh) {
+    if (threadIdx.x < a.n_sys) {
+        sh.done[threadIdx.x] = a.state[threadIdx.x].active ? 0 : 1;
+        sh.iters[threadIdx.x] = 0;
+        sh.beta[threadIdx.x] = 0.0;
+    }
+    for (int i = threadIdx.x; i < JF_MAX_SYS * MAXW; i += blockDim.x) sh.warp[i] = 0.0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cg_after_normb(const CgArgs &a, CgShared &sh) {
+    if (threadIdx.x < a.n_sys) {
+        const int s = threadIdx.x;
+        sh.normb[s] = sh.tot[s];
+        sh.resid[s] = sh.tot[s];
+        if (!sh.done[s] && sh.tot[s] == 0.0) sh.done[s] = 1;  // cg returns 0 when normb == 0
+    }
+    if (threadIdx.x == 0) {
+        int all = 1;
+        for (int s = 0; s < a.n_sys; s++) all &= (sh.done[s] || sh.tot[s] == 0.0);
+        sh.alldone = all;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cg_after_pAp(const CgArgs &a, CgShared &sh) {
+    if (threadIdx.x < a.n_sys && !sh.done[threadIdx.x]) sh.alpha[threadIdx.x] = sh.resid[threadIdx.x] / sh.tot[threadIdx.x];
+    __syncthreads();
+}
+
+// convergence test, beta, and the all-done flag for the next iteration (one barrier for all three)
+__device__ __forceinline__ void cg_after_rr(const CgArgs &a, CgShared &sh, long long it) {
+    if (threadIdx.x == 0) {
+        int all = 1;
+        for (int s = 0; s < a.n_sys; s++) {
+            if (!sh.done[s]) {
+                const double rsnew = sh.tot[s];
+                sh.iters[s] = (int)it;
+                if (rsnew < a.tol * sh.normb[s] || it == a.maxiter) {
+                    sh.done[s] = 1;
+                } else {
+                    sh.beta[s] = rsnew / sh.resid[s];
+                    sh.resid[s] = rsnew;
+                }
+            }
+            all &= sh.done[s];
+        }
+        sh.alldone = all;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cg_write_state(const CgArgs &a, CgShared &sh) {
+    if (blockIdx.x == 0 && threadIdx.x < a.n_sys && a.state[threadIdx.x].active) {
+        const int s = threadIdx.x;
+        a.state[s].cg_iters = sh.iters[s];
+        a.state[s].normb = sh.normb[s];
+        a.state[s].resid = sh.resid[s];
+        if (a.apply_update) a.state[s].du = a.step * a.step * sh.tot[s];
+    }
+}
+
+#define JF_BLOCK_FMA(vj, STRIDE, px, py, pz)  \
+    y0 = fma((vj)[0 * (STRIDE)], px, y0);     \
+    y0 = fma((vj)[1 * (STRIDE)], py, y0);     \
+    y0 = fma((vj)[2 * (STRIDE)], pz, y0);     \
+    y1 = fma((vj)[3 * (STRIDE)], px, y1);     \
+    y1 = fma((vj)[4 * (STRIDE)], py, y1);     \
+    y1 = fma((vj)[5 * (STRIDE)], pz, y1);     \
+    y2 = fma((vj)[6 * (STRIDE)], px, y2);     \
+    y2 = fma((vj)[7 * (STRIDE)], py, y2);     \
+    y2 = fma((vj)[8 * (STRIDE)], pz, y2);
+

@@ -1,0 +1,257 @@
+// Resident CG kernel: see jf_cg.cu for the overview of the CG design.
+//
+// One CTA owns `W` consecutive 32-row slices of ONE system for the whole solve:
+//   * their 3x3 blocks (W * wmax * 288 doubles) are staged once into shared memory,
+//   * x, r, p, Ap of a row live in the registers of the thread that owns the row,
+//   * each iteration the CTA first stages its HALO -- every distinct block column its slices
+//     touch, ~4x fewer than the references to them -- computing p_j = r_j + beta*pold_j once per
+//     node with coalesced-as-possible 256-bit loads, into shared memory; the block-row products
+//     then read p_j from shared memory through a 16-bit local column index.
+// The global gathers were what bounded the previous version (one L1tex wavefront per distinct line
+// per gather instruction: DESIGN.md K3); the halo cuts their number by the reuse factor.
+#include <algorithm>
+#include <vector>
+
+#include "jf_cg_common.cuh"
+
+namespace {
+constexpr int HALO_BATCH = 4;
+
+__global__ void __launch_bounds__(RES_WARPS * 32, 1) jf_cg_resident_kernel(CgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ CgShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    const int s = blockIdx.x / a.ctas_per_sys;
+    const int cb = blockIdx.x - s * a.ctas_per_sys;
+    const long long sl = (long long)cb * W + warp;
+    const bool have = sl < a.n_slices;
+    const long long row = sl * 32 + lane;
+    const long long vstride = a.Nf_pad * 4;
+    // shared-memory carve-up
+    double *mv_all = (double *)dyn_smem;                                   // W * wmax * 288
+    double *hv = mv_all + (size_t)W * a.wmax * 288;                        // hmax * 3
+    int *hn = (int *)(hv + (size_t)a.hmax * 3);                            // hmax
+    unsigned short *lc_all = (unsigned short *)(hn + a.hmax);              // W * wmax * 32
+    double *mv = mv_all + (size_t)warp * a.wmax * 288;
+    unsigned short *lc = lc_all + (size_t)warp * a.wmax * 32;
+    const int h0 = a.halo_ptr[cb], nh = a.halo_ptr[cb + 1] - h0;
+    unsigned epoch = 0;
+
+    cg_init_flags(a, sh);
+    const bool sys_on = !sh.done[s];
+
+    // stage once: matrix slice in SELL order (lane-contiguous), local column indices, halo node ids
+    int w = 0;
+    if (have && sys_on) {
+        const int q0 = a.slice_ptr[sl];
+        w = (a.slice_ptr[sl + 1] - q0) >> 5;
+        const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288;
+        for (int i = lane; i < w * 288; i += 32) mv[i] = v[i];
+        for (int j = 0; j < w; j++) lc[j * 32 + lane] = a.lcol[q0 + j * 32 + lane];
+    }
+    for (int h = threadIdx.x; h < nh; h += blockDim.x) hn[h] = a.halo_nodes[h0 + h];
+    __syncthreads();
+
+    double4 *const R4 = (double4 *)(a.r + s * vstride);
+    double4 *const Pa = (double4 *)(a.p0 + s * vstride);
+    double4 *const Pb = (double4 *)(a.p1 + s * vstride);
+    double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, y0 = 0, y1 = 0, y2 = 0;
+    double acc = 0.0;
+    if (have && sys_on) {
+        const double4 bv = ((const double4 *)(a.b + s * vstride))[row];
+        r0 = bv.x; r1 = bv.y; r2 = bv.z;
+        R4[row] = bv;
+        Pb[row] = make_double4(0.0, 0.0, 0.0, 0.0);
+        acc = r0 * r0 + r1 * r1 + r2 * r2;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.warp[s * MAXW + warp] = acc;
+    grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+    cg_after_normb(a, sh);
+
+    int cur = 0;
+#ifdef JF_CG_TIMING
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
+    for (long long it = 1; it <= a.maxiter; it++) {
+        if (sh.alldone) break;
+        TMARK(0);
+        const bool on = !sh.done[s];  // uniform over the CTA: all its slices belong to system s
+        acc = 0.0;
+        if (on) {
+            const double beta = sh.beta[s];
+            const double4 *Po = cur ? Pa : Pb;
+            double4 *Pn = cur ? Pb : Pa;
+            // ---- halo: p_j = r_j + beta * pold_j, once per distinct block column of this CTA ----------
+            for (int hb = threadIdx.x; hb < nh; hb += HALO_BATCH * blockDim.x) {
+                int node[HALO_BATCH];
+                double4 rv[HALO_BATCH], pv[HALO_BATCH];
+#pragma unroll
+                for (int k = 0; k < HALO_BATCH; k++) {
+                    const int h = hb + k * blockDim.x;
+                    node[k] = hn[h < nh ? h : hb];
+                }
+#pragma unroll
+                for (int k = 0; k < HALO_BATCH; k++) {
+                    rv[k] = ld_node(R4 + node[k]);
+                    pv[k] = ld_node(Po + node[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < HALO_BATCH; k++) {
+                    const int h = hb + k * blockDim.x;
+                    if (h < nh) {
+                        hv[3 * h] = fma(beta, pv[k].x, rv[k].x);
+                        hv[3 * h + 1] = fma(beta, pv[k].y, rv[k].y);
+                        hv[3 * h + 2] = fma(beta, pv[k].z, rv[k].z);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- block row: Ap_i = sum_j K_ij p_j, matrix and p_j from shared memory -------------------
+            if (have) {
+                y0 = y1 = y2 = 0.0;
+#pragma unroll 3
+                for (int j = 0; j < w; j++) {
+                    const double *pj = hv + 3 * (int)lc[j * 32 + lane];
+                    const double px = pj[0], py = pj[1], pz = pj[2];
+                    const double *vj = mv + j * 288 + lane;
+                    JF_BLOCK_FMA(vj, 32, px, py, pz)
+                }
+                p0 = fma(beta, p0, r0);
+                p1 = fma(beta, p1, r1);
+                p2 = fma(beta, p2, r2);
+                Pn[row] = make_double4(p0, p1, p2, 0.0);
+                acc = p0 * y0 + p1 * y1 + p2 * y2;
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sh.warp[s * MAXW + warp] = acc;
+        TMARK(1);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+        TMARK(2);
+
+        acc = 0.0;
+        if (on && have) {
+            const double alpha = sh.resid[s] / sh.tot[s];
+            x0 = fma(alpha, p0, x0);
+            x1 = fma(alpha, p1, x1);
+            x2 = fma(alpha, p2, x2);
+            r0 = fma(-alpha, y0, r0);
+            r1 = fma(-alpha, y1, r1);
+            r2 = fma(-alpha, y2, r2);
+            R4[row] = make_double4(r0, r1, r2, 0.0);
+            acc = r0 * r0 + r1 * r1 + r2 * r2;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sh.warp[s * MAXW + warp] = acc;
+        TMARK(3);
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+        TMARK(4);
+        cg_after_rr(a, sh, it);
+        cur ^= 1;
+        TMARK(5);
+    }
+#ifdef JF_CG_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("cg-res iters %d cycles/iter: top %.0f phaseA %.0f arA %.0f phaseB %.0f arB %.0f tail %.0f  (nh %d)\n", sh.iters[0],
+               (double)tacc[0] / sh.iters[0], (double)tacc[1] / sh.iters[0], (double)tacc[2] / sh.iters[0],
+               (double)tacc[3] / sh.iters[0], (double)tacc[4] / sh.iters[0], (double)tacc[5] / sh.iters[0], nh);
+#endif
+
+    // (A12) U[free] += step * x ; du = step^2 * sum x^2 ; x kept for jf_get_cg_solution
+    acc = 0.0;
+    if (have && a.state[s].active) {
+        ((double4 *)(a.x + s * vstride))[row] = make_double4(x0, x1, x2, 0.0);
+        if (a.apply_update && row < a.Nf) {
+            double *U = a.U + ((long long)s * a.N + row) * 3;
+            U[0] += a.step * x0;
+            U[1] += a.step * x1;
+            U[2] += a.step * x2;
+            acc = x0 * x0 + x1 * x1 + x2 * x2;
+        }
+    }
+    if (a.apply_update) {
+        acc = warp_sum(acc);
+        if (lane == 0) sh.warp[s * MAXW + warp] = acc;
+        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+    }
+    cg_write_state(a, sh);
+}
+
+size_t resident_smem(int W, int wmax, int hmax) {
+    return (size_t)W * wmax * 288 * sizeof(double) + (size_t)hmax * (3 * sizeof(double) + sizeof(int)) +
+           (size_t)W * wmax * 32 * sizeof(unsigned short);
+}
+}  // namespace
+
+// Decide whether the context's systems fit the resident kernel; if so build the per-CTA halo lists.
+// Returns 1 (resident configured), 0 (does not fit), or a negative jf_status.
+int jf_cg_resident_configure(jf_ctx *c) {
+    c->cg_resident = 0;
+    if (c->flags & JF_FLAG_NO_RESIDENT) return 0;
+    if (c->n_slices < 1 || c->n_sys > c->sm_count) return 0;
+    cudaFuncAttributes fa;
+    JF_CUDA(cudaFuncGetAttributes(&fa, jf_cg_resident_kernel));
+    int max_optin = 0;
+    JF_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const long long avail = (long long)max_optin - (long long)fa.sharedSizeBytes - 512;
+    // fewest warps per CTA such that all systems fit with one CTA per SM
+    const int ctas_budget = c->sm_count / c->n_sys;
+    if (ctas_budget < 1) return 0;
+    int W = (int)((c->n_slices + ctas_budget - 1) / ctas_budget);
+    if (W < 1) W = 1;
+    if (W > RES_WARPS) return 0;
+    const int ctas = (int)((c->n_slices + W - 1) / W);
+    // halo lists: sorted distinct block columns (incl. padding columns, which repeat the row) per CTA
+    std::vector<int32_t> hptr(ctas + 1, 0), hnodes;
+    std::vector<uint16_t> lcol((size_t)c->n_slots, 0);
+    int hmax = 1;
+    std::vector<int32_t> tmp;
+    for (int cb = 0; cb < ctas; cb++) {
+        const int64_t s0 = (int64_t)cb * W, s1 = std::min<int64_t>(c->n_slices, s0 + W);
+        const int64_t q0 = c->h_slice_ptr[s0], q1 = c->h_slice_ptr[s1];
+        tmp.assign(c->h_sell_col.begin() + q0, c->h_sell_col.begin() + q1);
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        if (tmp.size() > 65535) return 0;
+        for (int64_t q = q0; q < q1; q++)
+            lcol[q] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), c->h_sell_col[q]) - tmp.begin());
+        hnodes.insert(hnodes.end(), tmp.begin(), tmp.end());
+        hptr[cb + 1] = (int32_t)hnodes.size();
+        hmax = std::max(hmax, (int)tmp.size());
+    }
+    const size_t smem = resident_smem(W, c->cg_wmax, hmax);
+    if ((long long)smem > avail) return 0;
+    JF_CUDA(cudaFuncSetAttribute(jf_cg_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_resident_kernel, W * 32, smem));
+    if (per_sm < 1) return 0;
+    int rc;
+    if ((rc = jf_dev_alloc(c, &c->d_halo_ptr, hptr.size()))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_halo_nodes, hnodes.size()))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_lcol, lcol.size()))) return rc;
+    JF_CUDA(cudaMemcpy(c->d_halo_ptr, hptr.data(), hptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    JF_CUDA(cudaMemcpy(c->d_halo_nodes, hnodes.data(), hnodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    JF_CUDA(cudaMemcpy(c->d_lcol, lcol.data(), lcol.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    c->stats.bytes_h2d += (int64_t)(hptr.size() * 4 + hnodes.size() * 4 + lcol.size() * 2);
+    c->cg_resident = 1;
+    c->cg_res_warps = W;
+    c->cg_res_smem = smem;
+    c->cg_hmax = hmax;
+    c->cg_ctas_per_sys = ctas;
+    c->cg_grid = ctas * c->n_sys;
+    return 1;
+}
+
+int jf_cg_resident_launch(jf_ctx *c, CgArgs &a) {
+    a.halo_ptr = c->d_halo_ptr;
+    a.halo_nodes = c->d_halo_nodes;
+    a.lcol = c->d_lcol;
+    a.hmax = c->cg_hmax;
+    a.ctas_per_sys = c->cg_ctas_per_sys;
+    void *args[] = {&a};
+    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_resident_kernel, dim3(c->cg_grid), dim3(c->cg_res_warps * 32), args,
+                                        c->cg_res_smem, c->stream));
+    return 0;
+}

@@ -87,7 +87,9 @@ struct jf_ctx {
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
     unsigned int *d_barrier = nullptr; // grid barrier words
     int cg_grid = 0, elem_grid = 0;
-    int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0;
+    int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0, cg_hmax = 0, cg_ctas_per_sys = 0;
+    int32_t *d_halo_ptr = nullptr, *d_halo_nodes = nullptr;
+    uint16_t *d_lcol = nullptr;
     size_t cg_res_smem = 0;
 
     bool have_material = false, evaluated = false;
