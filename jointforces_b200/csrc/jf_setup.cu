@@ -9,7 +9,44 @@
 #include <numeric>
 #include <queue>
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
+#include <thread>
+
 #include "jf_internal.h"
+
+// JF_TIMING=1 in the environment prints the host-side setup stages to stderr
+struct StageTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    StageTimer() : on(getenv("JF_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[jf setup] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+// split [0,n) over host threads (structure build only; results do not depend on the thread count)
+template <typename F>
+static void parallel_for(int64_t n, F fn) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 16) nt = 16;
+    if (nt < 2 || n < 4096) {
+        fn((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t chunk = (n + nt - 1) / nt;
+    for (unsigned i = 0; i < nt; i++) {
+        const int64_t a = i * chunk, b = std::min<int64_t>(n, a + chunk);
+        if (a < b) th.emplace_back([=] { fn(a, b); });
+    }
+    for (auto &t : th) t.join();
+}
 
 // ------------------------------------------------------------------------------------------------
 // direction sphere, saenopy build_beams(300)
@@ -121,11 +158,13 @@ static void build_adjacency(int64_t N, int64_t T, const int32_t *tets, std::vect
         for (int m = 0; m < 4; m++)
             for (int r = 0; r < 4; r++) raw[fill[tets[4 * t + m]]++] = tets[4 * t + r];
     ptr.assign(N + 1, 0);
-    for (int64_t i = 0; i < N; i++) {
-        auto a = raw.begin() + cnt[i], b = raw.begin() + cnt[i + 1];
-        std::sort(a, b);
-        ptr[i + 1] = std::unique(a, b) - a;
-    }
+    parallel_for(N, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++) {
+            auto a = raw.begin() + cnt[i], b = raw.begin() + cnt[i + 1];
+            std::sort(a, b);
+            ptr[i + 1] = std::unique(a, b) - a;
+        }
+    });
     for (int64_t i = 0; i < N; i++) ptr[i + 1] += ptr[i];
     adj.resize((size_t)ptr[N]);
     for (int64_t i = 0; i < N; i++) std::copy(raw.begin() + cnt[i], raw.begin() + cnt[i] + (ptr[i + 1] - ptr[i]), adj.begin() + ptr[i]);
@@ -239,13 +278,17 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
             jf_set_error("tetrahedron %lld references node %d outside [0,%lld)", (long long)(i / 4), tets_in[i], (long long)N);
             return JF_ERR_ARG;
         }
+    StageTimer tm;
     int rc = build_dirtab(c, beams, n_beams);
     if (rc) return rc;
 
     std::vector<int64_t> aptr;
     std::vector<int32_t> adj;
+    tm.mark("validate+dirtab");
     build_adjacency(N, T, tets_in, aptr, adj);
+    tm.mark("adjacency");
     order_nodes(c, movable, aptr, adj);
+    tm.mark("ordering");
     const int64_t Nf = c->Nf;
     const std::vector<int32_t> &o2n = c->node_old2new;
 
@@ -269,6 +312,7 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
     for (int64_t i = 0; i < N; i++)
         for (int k = 0; k < 3; k++) xyz[3 * i + k] = nodes[3 * (int64_t)c->node_new2old[i] + k];
 
+    tm.mark("renumber tets");
     // shape tensors Phi = Chi * B^-1, V = |det B|/6  
     std::vector<double> phi((size_t)12 * T), vol(T);
     for (int64_t t = 0; t < T; t++) {
@@ -302,6 +346,7 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
         }
     }
 
+    tm.mark("shape tensors");
     // SELL-32 pattern over free rows / free columns, in new numbering
     c->n_slices = (Nf + JF_SLICE - 1) / JF_SLICE;
     c->Nf_pad = c->n_slices * JF_SLICE;
@@ -351,39 +396,41 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
         const int32_t *hit = std::lower_bound(a, b, col);
         return (int64_t)slice_ptr[row / JF_SLICE] + (hit - a) * JF_SLICE + row % JF_SLICE;
     };
+    tm.mark("SELL pattern");
     // gather lists for the stiffness: slot <- ((t*10+pair)*2+transpose), ascending t
     static const int pair_of[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
     if ((int64_t)T * 20 > 2000000000LL) {
         jf_set_error("mesh too large for 32-bit element offsets");
         return JF_ERR_ARG;
     }
-    std::vector<int32_t> cptr((size_t)c->n_slots + 1, 0);
-    for (int64_t t = 0; t < T; t++)
-        for (int m = 0; m < 4; m++) {
-            int32_t a = tets[4 * t + m];
-            if (a >= Nf) continue;
-            for (int r = 0; r < 4; r++) {
-                int32_t b = tets[4 * t + r];
-                if (b >= Nf) continue;
-                cptr[slot_of(a, b) + 1]++;
+    // slot of every (t, m, r) contribution, -1 if it touches a fixed node (parallel: independent lookups)
+    std::vector<int32_t> eslot((size_t)16 * T);
+    parallel_for(T, [&](int64_t lo, int64_t hi) {
+        for (int64_t t = lo; t < hi; t++)
+            for (int m = 0; m < 4; m++) {
+                const int32_t a = tets[4 * t + m];
+                for (int r = 0; r < 4; r++) {
+                    const int32_t b = tets[4 * t + r];
+                    eslot[16 * t + 4 * m + r] = (a < Nf && b < Nf) ? (int32_t)slot_of(a, b) : -1;
+                }
             }
-        }
+    });
+    // counting sort by slot, ascending t within a slot (deterministic summation order)
+    std::vector<int32_t> cptr((size_t)c->n_slots + 1, 0);
+    for (int64_t e = 0; e < 16 * T; e++)
+        if (eslot[e] >= 0) cptr[eslot[e] + 1]++;
     for (int64_t q = 0; q < c->n_slots; q++) cptr[q + 1] += cptr[q];
     std::vector<int32_t> csrc((size_t)cptr[c->n_slots]);
     {
         std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
         for (int64_t t = 0; t < T; t++)
-            for (int m = 0; m < 4; m++) {
-                int32_t a = tets[4 * t + m];
-                if (a >= Nf) continue;
+            for (int m = 0; m < 4; m++)
                 for (int r = 0; r < 4; r++) {
-                    int32_t b = tets[4 * t + r];
-                    if (b >= Nf) continue;
-                    int tr = m > r;
-                    csrc[fill[slot_of(a, b)]++] = (int32_t)(((t * 10 + pair_of[m][r]) << 1) | tr);
+                    const int32_t q = eslot[16 * t + 4 * m + r];
+                    if (q >= 0) csrc[fill[q]++] = (int32_t)(((t * 10 + pair_of[m][r]) << 1) | (m > r));
                 }
-            }
     }
+    tm.mark("stiffness gather lists");
     // gather lists for nodal forces: node <- (t*4+m)
     std::vector<int32_t> fptr(N + 1, 0);
     for (int64_t i = 0; i < 4 * T; i++) fptr[tets[i] + 1]++;
@@ -394,6 +441,7 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
         for (int64_t i = 0; i < 4 * T; i++) fsrc[fill[tets[i]]++] = (int32_t)i;
     }
 
+    tm.mark("force gather lists");
     if ((rc = upload(c, &c->d_tets, tets))) return rc;
     if ((rc = upload(c, &c->d_nodes, xyz))) return rc;
     if ((rc = upload(c, &c->d_phi, phi))) return rc;
@@ -404,6 +452,7 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
     if ((rc = upload(c, &c->d_contrib_src, csrc))) return rc;
     if ((rc = upload(c, &c->d_fn_ptr, fptr))) return rc;
     if ((rc = upload(c, &c->d_fn_src, fsrc))) return rc;
+    tm.mark("uploads");
     c->h_rowlen.resize(Nf);
     for (int64_t i = 0; i < Nf; i++) c->h_rowlen[i] = (int32_t)(rptr[i + 1] - rptr[i]);
     c->h_sell_col.swap(sell_col);
