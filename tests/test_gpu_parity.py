@@ -223,19 +223,45 @@ def test_golden_oracle_solutions(name, beams):
     assert np.allclose(out["relrec"][:, 1], g["relrec"][:, 1], rtol=1e-4)
 
 
-def test_resident_and_streaming_cg_agree(beams):
-    """Same arithmetic, different data placement (shared-memory/register resident vs streamed):
-    the two CG kernels must follow the same trajectory."""
+def test_resident_and_streaming_cg_agree(beams, monkeypatch):
+    """Same arithmetic, different data placement (matrix in registers / in shared memory / streamed
+    from global memory): the three CG kernels must follow the same trajectory."""
     from jointforces_b200 import _lib
     c = make_case(0.4, 100.0)
     res = []
-    for flags in (0, _lib.JF_FLAG_NO_RESIDENT):
+    for flags, no_regres in ((0, False), (0, True), (_lib.JF_FLAG_NO_RESIDENT, False)):
+        if no_regres:
+            monkeypatch.setenv("JF_CG_NO_REGRES", "1")
+        else:
+            monkeypatch.delenv("JF_CG_NO_REGRES", raising=False)
         with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams, flags=flags) as ctx:
             ctx.set_material(*COLLAGEN12)
             ctx.set_targets(c["f_target"])
             ctx.set_displacements(np.zeros_like(c["coords"]))
             relrec, cgit, n = ctx.relax(0.0033, 25, 0.01)
             res.append((ctx.displacements(), cgit[0], ctx.info()["cg_resident"]))
-    assert res[0][2] == 1 and res[1][2] == 0
-    assert np.abs(res[0][1].astype(int) - res[1][1]).max() <= 2
-    assert np.linalg.norm(res[0][0] - res[1][0]) / np.linalg.norm(res[1][0]) < 2e-5
+    assert [r[2] for r in res] == [2, 1, 0]
+    for other in res[:2]:
+        assert np.abs(other[1].astype(int) - res[2][1]).max() <= 2
+        assert np.linalg.norm(other[0] - res[2][0]) / np.linalg.norm(res[2][0]) < 2e-5
+
+
+def test_resident_batch_of_two_systems(beams):
+    """Two load cases small enough to be resident together (one CTA group per system)."""
+    from jointforces_b200 import _lib
+    cases = [make_case(0.667, p) for p in (10.0, 1000.0)]
+    singles = [_lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
+                                            COLLAGEN12, 0.0033, 30, 0.01, beams=beams) for c in cases]
+    c0 = cases[0]
+    with _lib.Context(c0["coords"], c0["tets"], c0["movable"], n_sys=2, beams=beams) as ctx:
+        assert ctx.info()["cg_resident"] in (1, 2)
+        ctx.set_material(*COLLAGEN12)
+        for s, c in enumerate(cases):
+            ctx.set_targets(c["f_target"], s)
+            ctx.set_displacements(np.zeros_like(c["coords"]), s)
+        relrec, cgit, n = ctx.relax(0.0033, 30, 0.01)
+        for s in range(2):
+            # the grid (hence the summation order of the dot products) differs from the single-system
+            # launch, so agreement is to rounding-amplified-by-CG level, not bitwise
+            assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= 2
+            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < 2e-5
