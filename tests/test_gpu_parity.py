@@ -227,7 +227,7 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
     """Same arithmetic, different data placement (matrix in registers / in shared memory / streamed
     from global memory): the three CG kernels must follow the same trajectory."""
     from jointforces_b200 import _lib
-    c = make_case(0.4, 100.0)
+    c = make_case(0.3, 100.0)
     res = []
     for flags, no_regres in ((0, False), (0, True), (_lib.JF_FLAG_NO_RESIDENT, False)):
         if no_regres:
@@ -240,7 +240,8 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
             ctx.set_displacements(np.zeros_like(c["coords"]))
             relrec, cgit, n = ctx.relax(0.0033, 25, 0.01)
             res.append((ctx.displacements(), cgit[0], ctx.info()["cg_resident"]))
-    assert [r[2] for r in res] == [2, 1, 0]
+    kinds = [r[2] for r in res]
+    assert kinds[0] in (1, 2) and kinds[1] == 1 and kinds[2] == 0, kinds   # 2 needs rows <= 18 blocks wide
     for other in res[:2]:
         assert np.abs(other[1].astype(int) - res[2][1]).max() <= 2
         assert np.linalg.norm(other[0] - res[2][0]) / np.linalg.norm(res[2][0]) < 2e-5
