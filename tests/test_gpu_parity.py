@@ -243,8 +243,9 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
     kinds = [r[2] for r in res]
     assert kinds[0] in (1, 2) and kinds[1] == 1 and kinds[2] == 0, kinds   # 2 needs rows <= 18 blocks wide
     for other in res[:2]:
-        assert np.abs(other[1].astype(int) - res[2][1]).max() <= 2
-        assert np.linalg.norm(other[0] - res[2][0]) / np.linalg.norm(res[2][0]) < 2e-5
+        # CG's loose stop makes the iteration count rounding-sensitive (DESIGN.md "Trajectory sensitivity")
+        assert np.abs(other[1].astype(int) - res[2][1]).max() <= 0.05 * res[2][1].max()
+        assert np.linalg.norm(other[0] - res[2][0]) / np.linalg.norm(res[2][0]) < 5e-5
 
 
 def test_resident_batch_of_two_systems(beams):
