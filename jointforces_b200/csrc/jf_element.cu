@@ -55,45 +55,52 @@ __host__ __device__ constexpr int sym2(int a, int b) {  // 00 11 22 01 02 12
     return a == b ? a : (a + b + 2);
 }
 
-// (A1): lambda -> w, w', w''.  exp-regimes share one expm1; for |x| < 1/8 a single polynomial
-// gives both expm1(x) and expm1(x) - x (needed without cancellation when d0 or ds is 1e30,
-// i.e. materials.linear, /root/reference/jointforces/materials.py:8).
-__device__ __forceinline__ void material_eval(const jf_material &m, double lam, double &w0, double &w1, double &w2) {
-    if (lam >= 0.0 && lam < m.ls) {
-        w2 = m.k;
-        w1 = m.k * lam;
-        w0 = 0.5 * m.k * lam * lam;
-        return;
-    }
-    const bool neg = lam < 0.0;
-    const double x = neg ? lam / m.d0 : (lam - m.ls) / m.ds;
-    double em, emx;
-    if (fabs(x) < 0.125) {
-        double p = 1.0 / 6227020800.0;
-        p = fma(p, x, 1.0 / 479001600.0);
-        p = fma(p, x, 1.0 / 39916800.0);
-        p = fma(p, x, 1.0 / 3628800.0);
-        p = fma(p, x, 1.0 / 362880.0);
-        p = fma(p, x, 1.0 / 40320.0);
-        p = fma(p, x, 1.0 / 5040.0);
-        p = fma(p, x, 1.0 / 720.0);
-        p = fma(p, x, 1.0 / 120.0);
-        p = fma(p, x, 1.0 / 24.0);
-        p = fma(p, x, 1.0 / 6.0);
-        p = fma(p, x, 0.5);
-        emx = p * x * x;
-        em = x + emx;
-    } else {
-        em = expm1(x);
+// per-material constants of (A1), formed once per tet
+struct MatC {
+    double k, ls, inv_d0, inv_ds, kd0, kd02, kds, kds2, kls, hkls2;
+    __device__ __forceinline__ explicit MatC(const jf_material &m)
+        : k(m.k), ls(m.ls), inv_d0(m.inv_d0), inv_ds(m.inv_ds), kd0(m.k * m.d0), kd02(m.k * m.d0 * m.d0), kds(m.k * m.ds),
+          kds2(m.k * m.ds * m.ds), kls(m.k * m.ls), hkls2(0.5 * m.k * m.ls * m.ls) {}
+};
+
+// (A1): lambda -> w, w', w''.  Both exponential regimes (buckling: x = lam/d0, stiffening:
+// x = (lam-ls)/ds) share one evaluation of em = expm1(x) and emx = expm1(x) - x: a single
+// polynomial gives both for |x| < 1/8 (no cancellation when d0 or ds is 1e30, i.e.
+// materials.linear, /root/reference/jointforces/materials.py:8; this is also the only path the
+// far field ever takes), exp(x) - 1 otherwise.  Selects instead of branches, one data-dependent
+// branch (the exp) that whole warps skip in the far field.
+__device__ __forceinline__ void material_eval(const MatC &m, double lam, double &w0, double &w1, double &w2) {
+    const bool neg = lam < 0.0, stf = lam >= m.ls;
+    const bool lin = !(neg || stf);
+    const double dl = lam - m.ls;
+    double x = neg ? lam * m.inv_d0 : dl * m.inv_ds;
+    if (lin) x = 0.0;
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, x, 1.0 / 479001600.0);
+    p = fma(p, x, 1.0 / 39916800.0);
+    p = fma(p, x, 1.0 / 3628800.0);
+    p = fma(p, x, 1.0 / 362880.0);
+    p = fma(p, x, 1.0 / 40320.0);
+    p = fma(p, x, 1.0 / 5040.0);
+    p = fma(p, x, 1.0 / 720.0);
+    p = fma(p, x, 1.0 / 120.0);
+    p = fma(p, x, 1.0 / 24.0);
+    p = fma(p, x, 1.0 / 6.0);
+    p = fma(p, x, 0.5);
+    double emx = p * x * x;
+    double em = x + emx;
+    if (fabs(x) >= 0.125) {
+        em = exp(x) - 1.0;
         emx = em - x;
     }
     w2 = m.k * (1.0 + em);
-    if (neg) {
-        w1 = m.k * m.d0 * em;
-        w0 = m.k * m.d0 * m.d0 * emx;
-    } else {
-        w1 = m.k * m.ls + m.k * m.ds * em;
-        w0 = 0.5 * m.k * m.ls * m.ls + m.k * m.ls * (lam - m.ls) + m.k * m.ds * m.ds * emx;
+    const double w1e = (neg ? m.kd0 : m.kds) * em;
+    const double w0e = (neg ? m.kd02 : m.kds2) * emx;
+    w1 = stf ? m.kls + w1e : w1e;
+    w0 = stf ? (m.hkls2 + m.kls * dl) + w0e : w0e;
+    if (lin) {
+        w1 = m.k * lam;
+        w0 = 0.5 * m.k * lam * lam;
     }
 }
 
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a
         const int s = (int)(item / a.T);
         const long long t = item - (long long)s * a.T;
         if (!a.state[s].active) continue;
-        const jf_material mat = a.mat[s];
+        const MatC mat(a.mat[s]);
         const int4 nd = a.tets[t];
         const double *phi = a.phi + 12 * t;
         double P[4][3];
