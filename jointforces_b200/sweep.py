@@ -50,12 +50,18 @@ def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, st
     if beams is None:
         beams = build_beams(300)
     n = len(bc_forces_list)
-    B = min(n, int(batch) if batch else MAX_BATCH, 64)
-    B = max(B, 1)
     mat = (material['K_0'], material['D_0'], material['L_S'], material['D_S'])
     results = [None] * n
     totals = None
     contexts = {}
+    if batch:
+        B = max(1, min(n, int(batch), 64))
+    else:
+        # meshes small enough for the resident CG kernel (matrix kept on chip for a whole CG solve) run fastest
+        # one load case at a time; larger ones amortise the grid barriers over a lockstep batch
+        contexts[1] = _lib.Context(coords, tets_i, movable, n_sys=1, beams=beams, device=device)
+        contexts[1].set_material(*mat)
+        B = 1 if contexts[1].info()["cg_resident"] else max(1, min(n, MAX_BATCH))
     try:
         for a in range(0, n, B):
             idx = list(range(a, min(n, a + B)))
