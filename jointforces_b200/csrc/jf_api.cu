@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <chrono>
 
@@ -70,9 +71,12 @@ static void ctx_free(jf_ctx *c) {
                     c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_halo_ptr, c->d_halo_nodes, c->d_lcol, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_partial,
                     c->d_barrier};
-    for (void *p : ptrs)
-        if (p) cudaFree(p);
-    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->stream) {
+        for (void *p : ptrs)
+            if (p) cudaFreeAsync(p, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    free(c->h_state);  // pageable on purpose: cudaMallocHost/cudaFreeHost cost up to ~90 ms per context
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -122,11 +126,21 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         for (auto &e : c->ev)
             if (cudaEventCreate(&e) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
         if (rc) break;
+        {   // keep freed workspace in the pool for the next context
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
         if ((rc = jf_build_structure(c, nodes, tets, movable, beams, n_beams))) break;
         const size_t S = (size_t)n_sys, N = (size_t)c->N, T = (size_t)c->T;
+        // (blocking cudaMemcpy/cudaMemset below run on the legacy stream; c->stream is non-blocking,
+        //  so every batch of stream-ordered allocations is followed by a stream synchronize)
         if ((rc = jf_dev_alloc(c, &c->d_mat, S))) break;
         if ((rc = jf_dev_alloc(c, &c->d_state, S))) break;
-        if (cudaMallocHost((void **)&c->h_state, S * sizeof(jf_sys_state)) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "pinned", __FILE__, __LINE__); break; }
+        c->h_state = (jf_sys_state *)malloc(S * sizeof(jf_sys_state));
+        if (!c->h_state) { jf_set_error("out of host memory"); rc = JF_ERR_NOMEM; break; }
         if ((rc = jf_dev_alloc(c, &c->d_U, S * N * 3))) break;
         if ((rc = jf_dev_alloc(c, &c->d_U0, S * N * 3))) break;
         if ((rc = jf_dev_alloc(c, &c->d_ft, S * N * 3))) break;
@@ -553,18 +567,27 @@ extern "C" int jf_solve_boundarycondition(int device, int64_t n_nodes, const dou
                                           int max_iter, double conv_crit, double *relrec, int32_t *cg_iters, int32_t *n_iter,
                                           double *forces_out, jf_stats *stats_out) {
     jf_ctx *c = nullptr;
+    const bool timing = getenv("JF_TIMING") != nullptr;
+    double t0 = now_ms(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
     int rc = jf_ctx_create(&c, device, 1, n_nodes, nodes, n_tets, tets, movable, n_beams, beams, 0);
     if (rc) return rc;
+    t1 = now_ms();
     do {
         if ((rc = jf_set_material(c, 0, k, d0, lambda_s, ds))) break;
         if ((rc = jf_set_targets(c, 0, f_target))) break;
         if ((rc = jf_set_displacements(c, 0, U))) break;
+        t2 = now_ms();
         if ((rc = jf_relax(c, step, max_iter, conv_crit, 0.0, relrec, cg_iters, n_iter))) break;
+        t3 = now_ms();
         if ((rc = jf_get_displacements(c, 0, U))) break;
         if (forces_out && (rc = jf_get_forces(c, 0, forces_out))) break;
         if (stats_out) jf_get_stats(c, stats_out);
+        t4 = now_ms();
     } while (0);
     jf_ctx_destroy(c);
+    if (timing)
+        fprintf(stderr, "[jf solve] create %.1f  set %.1f  relax %.1f  get %.1f  destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3,
+                now_ms() - t4);
     return rc;
 }
 

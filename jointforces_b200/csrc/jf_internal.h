@@ -115,8 +115,15 @@ template <typename Tp>
 int jf_dev_alloc(jf_ctx *c, Tp **p, size_t n) {
     size_t bytes = n * sizeof(Tp);
     if (bytes == 0) bytes = sizeof(Tp);
-    cudaError_t e = cudaMalloc((void **)p, bytes);
-    if (e != cudaSuccess) return jf_cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    // stream-ordered allocation from the device's default pool: jf_ctx_create raises the pool's release
+    // threshold, so a context created after another was destroyed reuses its memory instead of paying
+    // cudaMalloc/cudaFree (tens to hundreds of ms with high variance for ~35 buffers)
+    cudaError_t e = cudaMallocAsync((void **)p, bytes, c->stream);
+    if (e != cudaSuccess) return jf_cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    // setup copies use blocking calls on the legacy stream while c->stream is non-blocking: make the
+    // allocation visible to every stream before anyone touches it (idle stream: microseconds)
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return jf_cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
     c->bytes_device += (int64_t)bytes;
     return 0;
 }

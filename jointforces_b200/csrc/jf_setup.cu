@@ -249,8 +249,12 @@ static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int
             }
         }
         int64_t slots_id = 0, slots_cm = 0;
-        const double cost_id = gather_cost(order, N, ptr, adj, &slots_id);
-        const double cost_cm = gather_cost(cm, N, ptr, adj, &slots_cm);
+        double cost_id = 0, cost_cm = 0;
+        {
+            std::thread other([&] { cost_cm = gather_cost(cm, N, ptr, adj, &slots_cm); });
+            cost_id = gather_cost(order, N, ptr, adj, &slots_id);
+            other.join();
+        }
         // a gathered line and ~2 padded block slots cost about the same L1tex time
         if (cost_cm + 0.5 * (double)slots_cm / JF_SLICE < cost_id + 0.5 * (double)slots_id / JF_SLICE) order.swap(cm);
     }
@@ -315,7 +319,9 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
     tm.mark("renumber tets");
     // shape tensors Phi = Chi * B^-1, V = |det B|/6  
     std::vector<double> phi((size_t)12 * T), vol(T);
-    for (int64_t t = 0; t < T; t++) {
+    std::vector<int64_t> bad_tet(1, -1);
+    parallel_for(T, [&](int64_t lo_t, int64_t hi_t) {
+    for (int64_t t = lo_t; t < hi_t; t++) {
         const int32_t *n = &tets[4 * t];
         double B[3][3];
         for (int col = 0; col < 3; col++)
@@ -323,8 +329,8 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
         double det = B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[2][1]) - B[0][1] * (B[1][0] * B[2][2] - B[1][2] * B[2][0]) +
                      B[0][2] * (B[1][0] * B[2][1] - B[1][1] * B[2][0]);
         if (det == 0.0 || !isfinite(det)) {
-            jf_set_error("tetrahedron %d is degenerate (zero volume)", (int)torder[t]);
-            return JF_ERR_ARG;
+            bad_tet[0] = torder[t];  // any one of them will do for the message
+            continue;
         }
         double inv[3][3];
         inv[0][0] = (B[1][1] * B[2][2] - B[1][2] * B[2][1]) / det;
@@ -344,6 +350,11 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
             P[6 + j] = inv[1][j];
             P[9 + j] = inv[2][j];
         }
+    }
+    });
+    if (bad_tet[0] >= 0) {
+        jf_set_error("tetrahedron %d is degenerate (zero volume)", (int)bad_tet[0]);
+        return JF_ERR_ARG;
     }
 
     tm.mark("shape tensors");

@@ -267,3 +267,75 @@ def test_resident_batch_of_two_systems(beams):
             # launch, so agreement is to rounding-amplified-by-CG level, not bitwise
             assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= 2
             assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < 2e-5
+
+
+# ---- edge cases and error behaviour -----------------------------------------------------------------------
+def test_error_paths(beams):
+    from jointforces_b200 import _lib
+    nodes = np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]])
+    good = np.array([[0, 1, 2, 3], [1, 2, 3, 4]], np.int32)
+    mov = np.array([1, 1, 1, 1, 0], np.uint8)
+    with pytest.raises(_lib.JFError, match="outside"):
+        _lib.Context(nodes, np.array([[0, 1, 2, 7]], np.int32), mov)
+    flat = nodes.copy(); flat[:, 2] = 0
+    with pytest.raises(_lib.JFError, match="degenerate"):
+        _lib.Context(flat, good, mov)
+    with pytest.raises(_lib.JFError, match="n_sys"):
+        _lib.Context(nodes, good, mov, n_sys=1000)
+    with _lib.Context(nodes, good, mov, beams=beams) as ctx:
+        with pytest.raises(_lib.JFError, match="material"):
+            ctx.evaluate()
+        ctx.set_material(100.0, 1e30, 1e30, 1e30)
+        with pytest.raises(_lib.JFError, match="targets"):
+            ctx.relax(0.1, 3, 0.01)
+        with pytest.raises(_lib.JFError, match="before"):
+            ctx.forces()
+        with pytest.raises(_lib.JFError, match="system index"):
+            ctx.set_targets(np.zeros((5, 3)), sys=3)
+        with pytest.raises(_lib.JFError):
+            ctx.set_material(-1.0, 1.0, 1.0, 1.0)
+
+
+def test_degenerate_problems_do_not_crash(beams):
+    """All nodes fixed (no free rows), an orphan free node (empty stiffness row), zero load."""
+    from jointforces_b200 import _lib
+    nodes = np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1], [5, 5, 5]])
+    tets = np.array([[0, 1, 2, 3], [1, 2, 3, 4]], np.int32)
+    # all fixed
+    with _lib.Context(nodes, tets, np.zeros(6, np.uint8), beams=beams) as ctx:
+        ctx.set_material(100.0, 1e30, 1e30, 1e30)
+        ctx.set_targets(np.zeros((6, 3)))
+        U = np.zeros((6, 3)); U[4] = [0, 0, 0.01]
+        ctx.set_displacements(U)
+        relrec, cgit, n = ctx.relax(0.1, 3, 0.01)
+        assert np.array_equal(ctx.displacements(), U) and np.all(cgit[0] == 0)
+        assert relrec[0][-1, 1] > 0        # strain energy of the prescribed stretch
+    # node 5 is free but belongs to no tet; zero load -> nothing moves, CG returns at once
+    mov = np.array([1, 1, 1, 1, 0, 1], np.uint8)
+    with _lib.Context(nodes, tets, mov, beams=beams) as ctx:
+        ctx.set_material(100.0, 1e30, 1e30, 1e30)
+        ctx.set_targets(np.zeros((6, 3)))
+        ctx.set_displacements(np.zeros((6, 3)))
+        relrec, cgit, n = ctx.relax(0.1, 2, 0.0)
+        assert np.all(ctx.displacements() == 0) and np.all(cgit[0] == 0) and np.all(relrec[0][:, 1] == 0)
+        # and with a load on a connected node the orphan stays put while the others move
+        ft = np.zeros((6, 3)); ft[0] = [1e-3, 0, 0]
+        ctx.set_targets(ft)
+        ctx.set_displacements(np.zeros((6, 3)))
+        relrec, cgit, n = ctx.relax(0.5, 2, 0.0)
+        Uo = ctx.displacements()
+        assert np.all(Uo[5] == 0) and np.all(Uo[4] == 0) and np.abs(Uo[0]).max() > 0 and np.isfinite(Uo).all()
+
+
+def test_matches_oracle_on_structured_mesh_and_other_materials(beams):
+    """icoshell mesh (different connectivity pattern), fibrin (buckling only), high pressure (stiffening regime)."""
+    from jointforces_b200 import _lib
+    from oracle import c_oracle
+    for mat, p in ((FIBRIN, 30.0), (COLLAGEN12, 5000.0)):
+        case = make_case(0.667, p, method="icoshell")
+        ref = c_oracle.relax(case["coords"], case["tets"], case["movable"], case["f_target"], np.zeros_like(case["coords"]),
+                             beams, mat, 0.0033, 600, 0.01, nthreads=1)
+        out = _lib.solve_boundarycondition(case["coords"], case["tets"], case["movable"], case["f_target"],
+                                           np.zeros_like(case["coords"]), mat, 0.0033, 600, 0.01, beams=beams)
+        assert out["n_iter"] == ref["n_iter"]
+        assert np.linalg.norm(out["U"] - ref["U"]) / np.linalg.norm(ref["U"]) < 1e-4
