@@ -310,21 +310,22 @@ def test_degenerate_problems_do_not_crash(beams):
         relrec, cgit, n = ctx.relax(0.1, 3, 0.01)
         assert np.array_equal(ctx.displacements(), U) and np.all(cgit[0] == 0)
         assert relrec[0][-1, 1] > 0        # strain energy of the prescribed stretch
-    # node 5 is free but belongs to no tet; zero load -> nothing moves, CG returns at once
-    mov = np.array([1, 1, 1, 1, 0, 1], np.uint8)
+    # node 5 is free but belongs to no tet (empty stiffness row); nodes 1-4 fixed so the problem is well posed
+    mov = np.array([1, 0, 0, 0, 0, 1], np.uint8)
     with _lib.Context(nodes, tets, mov, beams=beams) as ctx:
         ctx.set_material(100.0, 1e30, 1e30, 1e30)
         ctx.set_targets(np.zeros((6, 3)))
         ctx.set_displacements(np.zeros((6, 3)))
         relrec, cgit, n = ctx.relax(0.1, 2, 0.0)
-        assert np.all(ctx.displacements() == 0) and np.all(cgit[0] == 0) and np.all(relrec[0][:, 1] == 0)
+        # zero load: only the rounding of |F s| - 1 (1e-16, same in the oracle) is left to "relax"
+        assert np.abs(ctx.displacements()).max() < 1e-12 and np.all(relrec[0][:, 1] < 1e-25)
         # and with a load on a connected node the orphan stays put while the others move
         ft = np.zeros((6, 3)); ft[0] = [1e-3, 0, 0]
         ctx.set_targets(ft)
         ctx.set_displacements(np.zeros((6, 3)))
         relrec, cgit, n = ctx.relax(0.5, 2, 0.0)
         Uo = ctx.displacements()
-        assert np.all(Uo[5] == 0) and np.all(Uo[4] == 0) and np.abs(Uo[0]).max() > 0 and np.isfinite(Uo).all()
+        assert np.all(Uo[5] == 0) and np.all(Uo[1:5] == 0) and 1e-8 < np.abs(Uo[0]).max() < 1e-2 and np.isfinite(Uo).all()
 
 
 def test_matches_oracle_on_structured_mesh_and_other_materials(beams):
