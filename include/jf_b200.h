@@ -104,6 +104,15 @@ int jf_get_cg_solution(jf_ctx *ctx, int sys, double *uu);
 int jf_relax(jf_ctx *ctx, double step, int max_iter, double conv_crit, double cg_tol, double *relrec,
              int32_t *cg_iters, int32_t *n_iter);
 
+/*
+ * Radial displacement curves on the device -- what extract_deformation_curve_solver computes on the host
+ * (simulation.py:296-299): per bin the median of |u|/r_inner over the nodes listed for that bin.
+ * The caller classifies the nodes once per mesh: bin_ptr (n_bins+1), bin_nodes (bin_ptr[n_bins]) in the caller's
+ * node numbering.  jf_get_curves fills curves (n_sys, n_bins); empty bins give NaN like np.nanmedian.
+ */
+int jf_set_curve_bins(jf_ctx *ctx, int n_bins, const int32_t *bin_ptr, const int32_t *bin_nodes, double r_inner);
+int jf_get_curves(jf_ctx *ctx, double *curves);
+
 /* accumulated device time (CUDA events on the context's stream) and work counters since creation
  * or the last jf_reset_stats */
 typedef struct jf_stats {

@@ -23,7 +23,7 @@ SYMBOLS = [
     "jf_last_error", "jf_version", "jf_device_count", "jf_ctx_create", "jf_ctx_destroy", "jf_set_material",
     "jf_set_targets", "jf_set_displacements", "jf_get_displacements", "jf_restore_displacements", "jf_get_forces", "jf_evaluate", "jf_get_energy",
     "jf_get_element_quantities", "jf_get_stiffness_blocks", "jf_cg", "jf_get_cg_solution", "jf_relax", "jf_get_stats",
-    "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64",
+    "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64", "jf_set_curve_bins", "jf_get_curves",
 ]
 
 
@@ -95,6 +95,8 @@ def load():
     L.jf_solve_boundarycondition.argtypes = [C.c_int, C.c_int64, _dp, C.c_int64, _ip, _bp, _dp, _dp, C.c_int, _vp] + \
         [C.c_double] * 4 + [C.c_double, C.c_int, C.c_double, _dp, _vp, _ip, _vp, C.POINTER(Stats)]
     L.jf_bench_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.jf_set_curve_bins.argtypes = [_vp, C.c_int, _ip, _vp, C.c_double]
+    L.jf_get_curves.argtypes = [_vp, _dp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("jf_last_error", "jf_ctx_destroy"):
@@ -220,6 +222,23 @@ class Context:
         check(self._L.jf_relax(self._h, float(step), int(max_iter), float(conv_crit), float(cg_tol), relrec, _ptr(cgit), n_iter))
         return ([relrec[s, : n_iter[s] + 1].copy() for s in range(self.n_sys)],
                 [cgit[s, : n_iter[s]].copy() for s in range(self.n_sys)], n_iter)
+
+    def set_curve_bins(self, coords, r_inner, x_edges):
+        """Classify the nodes into the radial bins [x_i, x_i+1) of |x|/r_inner with numpy's own comparisons
+        (reference simulation.py:296-299) and hand the per-bin node lists to the device."""
+        u = np.sqrt(np.sum(np.asarray(coords, dtype=np.float64) ** 2., axis=1)) / r_inner
+        x_edges = np.asarray(x_edges, dtype=np.float64)
+        lists = [np.nonzero((u >= x_edges[i]) & (u < x_edges[i + 1]))[0] for i in range(len(x_edges) - 1)]
+        ptr = np.zeros(len(lists) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(l) for l in lists])
+        nodes = np.ascontiguousarray(np.concatenate(lists) if ptr[-1] else np.zeros(0), dtype=np.int32)
+        self._n_bins = len(lists)
+        check(self._L.jf_set_curve_bins(self._h, len(lists), ptr, _ptr(nodes) if len(nodes) else None, float(r_inner)))
+
+    def curves(self):
+        out = np.empty((self.n_sys, self._n_bins))
+        check(self._L.jf_get_curves(self._h, out))
+        return out
 
     def stats(self):
         s = Stats()

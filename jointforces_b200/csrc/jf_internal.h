@@ -89,6 +89,11 @@ struct jf_ctx {
     int cg_grid = 0, elem_grid = 0;
     int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0, cg_hmax = 0, cg_ctas_per_sys = 0;
     int32_t *d_halo_ptr = nullptr, *d_halo_nodes = nullptr;
+    // radial curve extraction (jf_curves.cu)
+    int32_t *d_bin_ptr = nullptr, *d_bin_nodes = nullptr;
+    double *d_curve_scratch = nullptr, *d_curves = nullptr;
+    int n_bins = 0, bin_total = 0;
+    double curve_r_inner = 0.0;
     uint16_t *d_lcol = nullptr;
     size_t cg_res_smem = 0;
 

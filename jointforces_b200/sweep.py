@@ -35,10 +35,11 @@ def shard_indices(values, rank, world):
 
 
 def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, step, max_iter, conv_crit,
-                     initial_displacements=None, device=0, batch=None, beams=None):
+                     initial_displacements=None, device=0, batch=None, beams=None, curve_bins=None, fetch_fields=True):
     """Relax every load case in ``bc_forces_list`` (same mesh, same displacement conditions) and
     return a list of dicts ``U, forces, relrec, cg_iters`` in the same order, plus the summed
-    library statistics."""
+    library statistics.  ``curve_bins=(r_inner, x_edges)`` adds ``curve`` (radial median curve computed on the
+    device); ``fetch_fields=False`` then skips the download of U and forces altogether."""
     from .solver import build_beams
     coords = np.ascontiguousarray(coords, dtype=np.float64)
     tets_i = np.ascontiguousarray(tets).astype(np.int32)
@@ -61,6 +62,8 @@ def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, st
         # one load case at a time; larger ones amortise the grid barriers over a lockstep batch
         contexts[1] = _lib.Context(coords, tets_i, movable, n_sys=1, beams=beams, device=device)
         contexts[1].set_material(*mat)
+        if curve_bins is not None:
+            contexts[1].set_curve_bins(coords, *curve_bins)
         B = 1 if contexts[1].info()["cg_resident"] else max(1, min(n, MAX_BATCH))
     try:
         for a in range(0, n, B):
@@ -69,14 +72,21 @@ def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, st
             if size not in contexts:
                 contexts[size] = _lib.Context(coords, tets_i, movable, n_sys=size, beams=beams, device=device)
                 contexts[size].set_material(*mat)
+                if curve_bins is not None:
+                    contexts[size].set_curve_bins(coords, *curve_bins)
             ctx = contexts[size]
             ctx.reset_stats()
             for s, i in enumerate(idx):
                 ctx.set_targets(np.nan_to_num(bc_forces_list[i]), s)
                 ctx.set_displacements(U0, s)
             relrec, cgit, _ = ctx.relax(step, max_iter, conv_crit)
+            curves = ctx.curves() if curve_bins is not None else None
             for s, i in enumerate(idx):
-                results[i] = dict(U=ctx.displacements(s), forces=ctx.forces(s), relrec=relrec[s], cg_iters=cgit[s])
+                results[i] = dict(relrec=relrec[s], cg_iters=cgit[s])
+                if fetch_fields:
+                    results[i].update(U=ctx.displacements(s), forces=ctx.forces(s))
+                if curves is not None:
+                    results[i]['curve'] = curves[s]
             st = ctx.stats()
             totals = st if totals is None else {k: totals[k] + st[k] for k in st}
     finally:
@@ -105,15 +115,17 @@ def run_sweep(meshfile, outfolder, values, material, var_arg='pressure', max_ite
     mine = shard_indices(values, rank, world)
     bcs = [sim.spherical_boundary_conditions(coords, r_in, r_out, float(values[i])) for i in mine]
     results, stats = ([], None)
+    x, x_center = sim.lookup_bins(x0, x1, n_bins)
+    # the radius exactly as the table builder recovers it from parameters.txt (simulation.py:296-297)
+    r_curve = (r_in * 1e6) * 10 ** -6
     if len(mine):
         results, stats = relax_load_cases(coords, tets, bcs[0]['displacement'], [b['forces'] for b in bcs], material, step,
-                                          max_iter, conv_crit, device=device, batch=batch)
-    x, x_center = sim.lookup_bins(x0, x1, n_bins)
+                                          max_iter, conv_crit, device=device, batch=batch, curve_bins=(r_curve, x),
+                                          fetch_fields=write)
     curves = np.full((len(mine), n_bins), np.nan)
     mat_par = SemiAffineFiberMaterial(material['K_0'], material['D_0'], material['L_S'], material['D_S']).serialize()
     for j, (i, bc, res) in enumerate(zip(mine, bcs, results)):
-        # the radius exactly as the table builder recovers it from parameters.txt (simulation.py:296-297)
-        curves[j] = sim.radial_median_curve(coords, res['U'], (r_in * 1e6) * 10 ** -6, x)
+        curves[j] = res['curve']   # radial median on the device (jf_curves.cu), bit-identical to the host formula
         if write:
             folder = outfolder + '/simulation' + str(int(i)).zfill(6)
             os.makedirs(folder, exist_ok=True)

@@ -73,3 +73,30 @@ def test_distribute_solver_layout_and_table(meshfile, tmp_path, beams):
     xs = table['x'][populated][2]
     d = float(get_displacement(xs, 50.0))
     assert abs(float(get_pressure(xs, d)) / 50.0 - 1) < 0.02
+
+
+def test_device_curves_equal_host_formula_bitwise(beams):
+    """jf_get_curves vs the reference's numpy expression (simulation.py:296-299) on the same displacements."""
+    from jointforces_b200 import _lib
+    from jointforces_b200.mesh import generate_spherical_inclusion
+    coords, tets = generate_spherical_inclusion(lf_iso=0.3)
+    rng = np.random.default_rng(4)
+    coords = coords * (1 + 0.2 * rng.random((len(coords), 1)))       # scatter the radii so that many bins are populated
+    r_in = (100 * 10 ** -6 * 1e6) * 10 ** -6
+    movable = np.linalg.norm(coords, axis=1) < 0.9e-2
+    x, _ = jf.simulation.lookup_bins()
+    with _lib.Context(coords, tets.astype(np.int32), movable, n_sys=2, beams=beams) as ctx:
+        ctx.set_curve_bins(coords, r_in, x)
+        Us = [rng.normal(size=coords.shape) * 1e-6, rng.normal(size=coords.shape) * 1e-5]
+        Us[1][::7] = Us[1][1::7][: len(Us[1][::7])]                   # exact ties
+        for s, U in enumerate(Us):
+            ctx.set_displacements(U, s)
+        got = ctx.curves()
+    for s, U in enumerate(Us):
+        u = np.sqrt(np.sum(coords ** 2., axis=1)) / r_in
+        v = np.sqrt(np.sum(U ** 2., axis=1)) / r_in
+        with np.errstate(all="ignore"):
+            expect = np.array([np.nanmedian(v[(u >= x[i]) & (u < x[i + 1])]) for i in range(len(x) - 1)])
+        assert (~np.isnan(expect)).sum() > 40
+        assert np.array_equal(np.isnan(got[s]), np.isnan(expect))
+        assert np.array_equal(got[s][~np.isnan(expect)], expect[~np.isnan(expect)])
