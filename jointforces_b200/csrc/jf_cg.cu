@@ -31,6 +31,8 @@
 //
 // Matrix: SELL-32 3x3 blocks (jf_assembly.cu); one thread owns one block row.  Vectors are
 // (row,4) doubles so a gathered node is one 32-byte sector.
+#include <stdlib.h>
+
 #include "jf_cg_common.cuh"
 
 int jf_cg_resident_configure(jf_ctx *c);
@@ -60,6 +62,11 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.p1 = c->d_p1;
     a.Ap = c->d_Ap;
     a.partial = c->d_partial;
+    // measured in the real kernel on config 2: 7.29 us/iteration with it, 6.78 us with the cooperative barrier (the
+    // isolated micro-benchmark says the opposite: 1.6 vs 2.05 us) -- off unless JF_CG_SUMS_ONLY=1
+    a.sums_only = getenv("JF_CG_SUMS_ONLY") ? atoi(getenv("JF_CG_SUMS_ONLY")) : 0;
+    a.sync_ctr = c->d_sync;
+    a.sum_slots = (ulonglong2 *)(c->d_sync + 4);
     a.state = c->d_state;
     a.U = c->d_U;
     a.N = c->N;
@@ -73,6 +80,8 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.maxiter = maxiter;
     a.step = step;
     a.apply_update = apply_update;
+    // counter and flag words of the sums-only barrier restart at zero in every launch (a few KB, same stream)
+    JF_CUDA(cudaMemsetAsync(c->d_sync, 0, 16 + (size_t)2 * c->n_sys * c->cg_grid * sizeof(ulonglong2), c->stream));
     int rc = c->cg_resident ? jf_cg_resident_launch(c, a) : jf_cg_stream_launch(c, a);
     if (rc) return rc;
     c->stats.kernel_launches++;

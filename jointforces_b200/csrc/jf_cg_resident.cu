@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(RES_WARPS * 32, 1) jf_cg_resident_kernel(CgArg
     double *mv = mv_all + (size_t)warp * a.wmax * 288;
     unsigned short *lc = lc_all + (size_t)warp * a.wmax * 32;
     const int h0 = a.halo_ptr[cb], nh = a.halo_ptr[cb + 1] - h0;
-    unsigned epoch = 0;
+    unsigned epoch = 0, nsum = 0;
 
     cg_init_flags(a, sh);
     const bool sys_on = !sh.done[s];
@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(RES_WARPS * 32, 1) jf_cg_resident_kernel(CgArg
         acc = warp_sum(acc);
         if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         TMARK(1);
-        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+        if (a.sums_only) grid_allreduce_sums_only(a, sh.warp, sh.tot, nsum);
+        else grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
         TMARK(2);
 
         acc = 0.0;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_regres_kernel(CgArgs a) {
     double *hv = (double *)dyn_smem;               // hmax * 3
     int *hn = (int *)(hv + (size_t)a.hmax * 3);    // hmax
     const int h0 = a.halo_ptr[cb], nh = a.halo_ptr[cb + 1] - h0;
-    unsigned epoch = 0;
+    unsigned epoch = 0, nsum = 0;
 
     cg_init_flags(a, sh);
     const bool sys_on = !sh.done[s];
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(256, 1) jf_cg_regres_kernel(CgArgs a) {
         acc = warp_sum(acc);
         if (lane == 0) sh.warp[s * MAXW + warp] = acc;
         TMARK(1);
-        grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
+        if (a.sums_only) grid_allreduce_sums_only(a, sh.warp, sh.tot, nsum);
+        else grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
         TMARK(2);
 
         acc = 0.0;

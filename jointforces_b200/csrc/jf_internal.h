@@ -85,7 +85,8 @@ struct jf_ctx {
     int64_t Nf_pad = 0;
     double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_p0 = nullptr, *d_p1 = nullptr, *d_Ap = nullptr;
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
-    unsigned int *d_barrier = nullptr; // grid barrier words
+    unsigned int *d_barrier = nullptr; // (unused)
+    unsigned int *d_sync = nullptr;    // sums-only barrier: counter (16 B) + (2, S, grid) 16-byte slots
     int cg_grid = 0, elem_grid = 0;
     int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0, cg_hmax = 0, cg_ctas_per_sys = 0;
     int32_t *d_halo_ptr = nullptr, *d_halo_nodes = nullptr;

@@ -44,6 +44,29 @@ __global__ void bench(ulonglong2 *slots, double *partial, double *out, int iters
             grid.sync();
             if (warp == 0) { double t = 0; for (int i = lane; i < gridDim.x; i += 32) t += __ldcg(partial + (it & 1) * gridDim.x + i); t = warp_sum(t); if (lane == 0) s_tot = t; }
             __syncthreads();
+        } else if (MODE == 3) {  // counter barrier that only carries the sums: no memory fences at all
+            epoch++;
+            __syncthreads();
+            if (warp == 0) {
+                double t = lane < nwarps ? s_warp[lane] : 0; t = warp_sum(t);
+                unsigned *ctr = (unsigned *)slots;   // monotone arrival counter
+                double *pp = partial + (epoch & 1) * gridDim.x;
+                if (lane == 0) {
+                    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(pp + blockIdx.x), "d"(t) : "memory");
+                    if (FENCE == 1) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(ctr) : "memory");
+                    else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(ctr) : "memory");
+                    unsigned seen;
+                    const unsigned target = epoch * gridDim.x;
+                    do { if (FENCE == 1) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+                         else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory"); } while (seen < target);
+                }
+                __syncwarp();
+                double u = 0;
+                for (int i = lane; i < gridDim.x; i += 32) { double x; asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(x) : "l"(pp + i) : "memory"); u += x; }
+                u = warp_sum(u);
+                if (lane == 0) s_tot = u;
+            }
+            __syncthreads();
         } else {          // flag-carrying slots
             epoch++;
             ulonglong2 *sl = slots + (size_t)(epoch & 1u) * gridDim.x;
@@ -106,12 +129,13 @@ float run(int grid, int block, int iters) {
 
 int main() {
     const int iters = 20000;
-    int grids[] = {134, 148, 296}, blocks[] = {128, 512};
+    int grids[] = {134, 148}, blocks[] = {128, 256};
     printf("us per barrier+allreduce   grid block  coopgroups  slots+sc-fence  slots+acqrel  slots+nofence | parallel-poll: sc acqrel nofence\n");
     for (int g : grids) for (int b : blocks) {
         if (g * b > 148 * 2048) continue;
         printf("%5d %5d   %8.2f   %8.2f   %8.2f   %8.2f", g, b, run<0, 1>(g, b, iters), run<1, 1>(g, b, iters), run<1, 2>(g, b, iters), run<1, 0>(g, b, iters));
-        printf("                                                                         | %8.2f   %8.2f   %8.2f\n", run<2, 1>(g, b, iters), run<2, 2>(g, b, iters), run<2, 0>(g, b, iters));
+        printf(" | %8.2f   %8.2f   %8.2f", run<2, 1>(g, b, iters), run<2, 2>(g, b, iters), run<2, 0>(g, b, iters));
+        printf(" | counter, sums only: rel/acq %8.2f  relaxed %8.2f\n", run<3, 1>(g, b, iters), run<3, 0>(g, b, iters));
     }
     return 0;
 }
