@@ -92,6 +92,8 @@ int jf_get_stiffness_blocks(jf_ctx *ctx, int sys, int64_t *n_blocks, int32_t *ro
  * iters: (n_sys).  Solution via jf_get_cg_solution (n_nodes,3; zero on fixed nodes). */
 int jf_cg(jf_ctx *ctx, double tol, int64_t maxiter, int32_t *iters);
 int jf_get_cg_solution(jf_ctx *ctx, int sys, double *uu);
+/* parity hook: y (n_nodes,3) = K_glo x with the stiffness of the last evaluation (free rows and columns only) */
+int jf_apply_stiffness(jf_ctx *ctx, int sys, const double *x, double *y);
 
 /*
  * Replaces solve_boundarycondition(step_size, max_iterations, rel_conv_crit) (simulation.py:167;

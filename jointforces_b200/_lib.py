@@ -23,7 +23,7 @@ SYMBOLS = [
     "jf_last_error", "jf_version", "jf_device_count", "jf_ctx_create", "jf_ctx_destroy", "jf_set_material",
     "jf_set_targets", "jf_set_displacements", "jf_get_displacements", "jf_restore_displacements", "jf_get_forces", "jf_evaluate", "jf_get_energy",
     "jf_get_element_quantities", "jf_get_stiffness_blocks", "jf_cg", "jf_get_cg_solution", "jf_relax", "jf_get_stats",
-    "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64", "jf_set_curve_bins", "jf_get_curves",
+    "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64", "jf_set_curve_bins", "jf_get_curves", "jf_apply_stiffness",
 ]
 
 
@@ -95,6 +95,7 @@ def load():
     L.jf_solve_boundarycondition.argtypes = [C.c_int, C.c_int64, _dp, C.c_int64, _ip, _bp, _dp, _dp, C.c_int, _vp] + \
         [C.c_double] * 4 + [C.c_double, C.c_int, C.c_double, _dp, _vp, _ip, _vp, C.POINTER(Stats)]
     L.jf_bench_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.jf_apply_stiffness.argtypes = [_vp, C.c_int, _dp, _dp]
     L.jf_set_curve_bins.argtypes = [_vp, C.c_int, _ip, _vp, C.c_double]
     L.jf_get_curves.argtypes = [_vp, _dp]
     for name in SYMBOLS:
@@ -209,6 +210,11 @@ class Context:
         it = np.zeros(self.n_sys, np.int32)
         check(self._L.jf_cg(self._h, float(tol), int(maxiter), it))
         return it
+
+    def apply_stiffness(self, x, sys=0):
+        out = np.empty((self.N, 3))
+        check(self._L.jf_apply_stiffness(self._h, int(sys), np.ascontiguousarray(x, dtype=np.float64), out))
+        return out
 
     def cg_solution(self, sys=0):
         out = np.empty((self.N, 3))

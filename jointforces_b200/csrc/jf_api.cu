@@ -435,6 +435,14 @@ extern "C" int jf_cg(jf_ctx *c, double tol, int64_t maxiter, int32_t *iters) {
     return JF_OK;
 }
 
+extern "C" int jf_apply_stiffness(jf_ctx *c, int sys, const double *x, double *y) {
+    CHECK_CTX(c);
+    CHECK_SYS(c, sys);
+    if (!x || !y) { jf_set_error("null argument"); return JF_ERR_ARG; }
+    if (!c->evaluated) { jf_set_error("jf_apply_stiffness before jf_evaluate"); return JF_ERR_STATE; }
+    return jf_spmv_host(c, sys, x, y);
+}
+
 extern "C" int jf_get_cg_solution(jf_ctx *c, int sys, double *uu) {
     CHECK_CTX(c);
     CHECK_SYS(c, sys);

@@ -6,6 +6,10 @@
 // Stiffness layout (SELL-32 by block rows): slot q = slice_ptr[k] + 32*j + lane holds the j-th
 // block of row 32*k+lane; its nine values live at val[(q>>5)*288 + 32*comp + (q&31)], so a warp
 // that owns a slice reads every component as one 256-byte coalesced line.
+#include <string.h>
+
+#include <vector>
+
 #include "jf_internal.h"
 
 namespace {
@@ -110,7 +114,53 @@ __global__ void __launch_bounds__(1024) jf_reduce_kernel(const double *__restric
     }
 }
 
+// y = K x for one system, one thread per block row (parity hook: jf_apply_stiffness; the CG kernels have their own SpMV)
+__global__ void __launch_bounds__(128) jf_spmv_kernel(const int32_t *__restrict__ slice_ptr, const int32_t *__restrict__ sell_col,
+                                                      const double *__restrict__ val, const double *__restrict__ x4,
+                                                      double *__restrict__ y4, long long n_slices) {
+    const long long sl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (sl >= n_slices) return;
+    const int lane = threadIdx.x & 31;
+    const int q0 = slice_ptr[sl], w = (slice_ptr[sl + 1] - q0) >> 5;
+    const double *v = val + (long long)(q0 >> 5) * 288 + lane;
+    double y0 = 0, y1 = 0, y2 = 0;
+    for (int j = 0; j < w; j++) {
+        const double *xj = x4 + 4ll * sell_col[q0 + 32 * j + lane];
+        const double *vj = v + 288 * j;
+        y0 += vj[0] * xj[0] + vj[32] * xj[1] + vj[64] * xj[2];
+        y1 += vj[96] * xj[0] + vj[128] * xj[1] + vj[160] * xj[2];
+        y2 += vj[192] * xj[0] + vj[224] * xj[1] + vj[256] * xj[2];
+    }
+    double *yo = y4 + 4 * (sl * 32 + lane);
+    yo[0] = y0;
+    yo[1] = y1;
+    yo[2] = y2;
+    yo[3] = 0.0;
+}
+
 }  // namespace
+
+// y (N,3) = K x (N,3) with the assembled stiffness of the last evaluation; rows/columns of fixed nodes are zero
+int jf_spmv_host(jf_ctx *c, int sys, const double *x, double *y) {
+    std::vector<double> xin((size_t)c->Nf_pad * 4, 0.0), yout((size_t)c->Nf_pad * 4, 0.0);
+    for (int64_t i = 0; i < c->Nf; i++)
+        for (int k = 0; k < 3; k++) xin[4 * i + k] = x[3 * (int64_t)c->node_new2old[i] + k];
+    // reuse the CG work vectors p0 (in) and Ap (out) of this system
+    double *dx = c->d_p0 + (size_t)sys * c->Nf_pad * 4, *dy = c->d_Ap + (size_t)sys * c->Nf_pad * 4;
+    JF_CUDA(cudaMemcpyAsync(dx, xin.data(), xin.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (c->n_slices > 0) {
+        jf_spmv_kernel<<<(unsigned)((c->n_slices + 3) / 4), 128, 0, c->stream>>>(c->d_slice_ptr, c->d_sell_col,
+                                                                                   c->d_val + (size_t)sys * c->n_slots * 9, dx, dy, c->n_slices);
+        JF_CUDA(cudaGetLastError());
+        c->stats.kernel_launches++;
+    }
+    JF_CUDA(cudaMemcpyAsync(yout.data(), dy, yout.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    memset(y, 0, (size_t)c->N * 3 * sizeof(double));
+    for (int64_t i = 0; i < c->Nf; i++)
+        for (int k = 0; k < 3; k++) y[3 * (int64_t)c->node_new2old[i] + k] = yout[4 * i + k];
+    return 0;
+}
 
 int jf_launch_assembly(jf_ctx *c) {
     dim3 gk((unsigned)((c->n_slots + 255) / 256), (unsigned)c->n_sys);

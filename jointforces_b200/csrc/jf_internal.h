@@ -113,6 +113,7 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets, cons
 // kernels (each returns after enqueueing on c->stream)
 int jf_launch_element(jf_ctx *c);
 int jf_launch_assembly(jf_ctx *c);
+int jf_spmv_host(jf_ctx *c, int sys, const double *x, double *y);
 int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_update);
 int jf_cg_configure(jf_ctx *c);
 int jf_elem_configure(jf_ctx *c);

@@ -1,0 +1,91 @@
+"""Size-independent properties at BASELINE's larger sizes, where the CPU oracle would take tens of
+minutes: Newton's third law (internal forces sum to zero), force = -dE/dU and K = -1/2 df/dU by
+directional finite differences, symmetry of K, the streaming CG kernel against its own residual, and
+scale invariance of the whole relaxation for the linear material."""
+import numpy as np
+import pytest
+
+from conftest import COLLAGEN12, LINEAR
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big_case():
+    from jointforces_b200.mesh import generate_spherical_inclusion
+    from jointforces_b200.simulation import spherical_boundary_conditions
+    coords, tets = generate_spherical_inclusion(length_factor=0.03)      # BASELINE configs[3]: 78,057 nodes / 460,172 tets
+    assert len(coords) == 78057 and len(tets) == 460172
+    bc = spherical_boundary_conditions(coords, 100e-6, 10000e-6, 10000.0)
+    movable = np.any(np.isnan(bc["displacement"]), axis=1)
+    return dict(coords=coords, tets=tets.astype(np.int32), movable=movable, ft=np.nan_to_num(bc["forces"]))
+
+
+def _field(case, scale, seed):
+    rng = np.random.default_rng(seed)
+    r = np.linalg.norm(case["coords"], axis=1)
+    U = rng.normal(size=case["coords"].shape) * (scale * r)[:, None]
+    U[~case["movable"]] = 0
+    return U
+
+
+def test_fullsize_force_balance_and_derivatives(big_case, beams):
+    from jointforces_b200 import _lib
+    c = big_case
+    U = _field(c, 2e-2, 0)            # strains of a few percent: all three regimes of collagen12 are populated
+    d = _field(c, 1.0, 1)
+    d /= np.abs(d).max()
+    eps = 1e-6 * np.linalg.norm(c["coords"], axis=1).min()
+    with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams) as ctx:
+        assert ctx.info()["cg_resident"] == 0
+        ctx.set_material(*COLLAGEN12)
+        ctx.set_targets(c["ft"])
+        ctx.set_displacements(U); ctx.evaluate()
+        f0 = ctx.forces(); e0 = ctx.energy()[0]
+        Kd = ctx.apply_stiffness(d)
+        KTd_dot = None
+        # Newton's third law: every element's nodal forces cancel, so the global sum vanishes
+        assert np.abs(f0.sum(0)).max() < 1e-9 * np.abs(f0).sum()
+        ctx.set_displacements(U + eps * d); ctx.evaluate()
+        fp = ctx.forces(); ep = ctx.energy()[0]
+        ctx.set_displacements(U - eps * d); ctx.evaluate()
+        fm = ctx.forces(); em = ctx.energy()[0]
+        # f = -dE/dU along d
+        assert abs((ep - em) / (2 * eps) + np.sum(f0 * d)) < 1e-5 * abs(np.sum(f0 * d))
+        # K = -1/2 df/dU (the half Hessian saenopy solves with), on the free rows
+        free = c["movable"]
+        lhs = (fp - fm)[free] / (2 * eps)
+        assert np.linalg.norm(lhs + 2 * Kd[free]) < 1e-5 * np.linalg.norm(2 * Kd[free])
+        # symmetry: d2 . K d == d . K d2
+        ctx.set_displacements(U); ctx.evaluate()
+        d2 = _field(c, 1.0, 2)
+        a = np.sum(d2 * ctx.apply_stiffness(d)); b = np.sum(d * ctx.apply_stiffness(d2))
+        assert abs(a - b) < 1e-10 * max(abs(a), abs(b))
+        # streaming CG: the returned x must satisfy |b - K x|^2 < tol |b|^2 with b = f - f_target
+        it = ctx.cg(1e-5)
+        x = ctx.cg_solution()
+        bvec = (ctx.forces() - c["ft"]) * free[:, None]
+        res = bvec - ctx.apply_stiffness(x)
+        assert 0 < it[0] < 3 * len(free)
+        assert np.sum(res ** 2) < 1.05e-5 * np.sum(bvec ** 2)
+        assert e0 > 0
+
+
+def test_fullsize_relaxation_scales_with_load_for_linear_material(big_case, beams):
+    """materials.linear at tiny loads is a linear problem and every stopping test of the algorithm is scale
+    invariant, so 2.5x the load must give 2.5x the displacements after the same number of Newton and CG
+    iterations -- through element kernel, assembly, streaming CG and the driver at full size."""
+    from jointforces_b200 import _lib
+    c = big_case
+    with _lib.Context(c["coords"], c["tets"], c["movable"], n_sys=2, beams=beams) as ctx:
+        ctx.set_material(*LINEAR)
+        ctx.set_targets(c["ft"] * 1e-4, 0)
+        ctx.set_targets(c["ft"] * 2.5e-4, 1)
+        ctx.set_displacements(np.zeros_like(c["coords"]), 0)
+        ctx.set_displacements(np.zeros_like(c["coords"]), 1)
+        relrec, cgit, n = ctx.relax(0.066, 12, 0.01)
+        U0, U1 = ctx.displacements(0), ctx.displacements(1)
+    assert n[0] == n[1] == 12
+    assert np.abs(cgit[0].astype(int) - cgit[1]).max() <= 2
+    assert np.linalg.norm(U1 - 2.5 * U0) < 2e-4 * np.linalg.norm(U1)
+    assert np.allclose(relrec[1][:, 1], 6.25 * relrec[0][:, 1], rtol=1e-3)
