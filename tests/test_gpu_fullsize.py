@@ -22,9 +22,12 @@ def big_case():
 
 
 def _field(case, scale, seed):
+    """A smooth field (uniform strain `scale` from a random affine map) plus 0.1 % node-level noise: a rough
+    field would put the Delaunay slivers (quality ~1e-3) at strains where exp((lam-ls)/ds) overflows."""
     rng = np.random.default_rng(seed)
-    r = np.linalg.norm(case["coords"], axis=1)
-    U = rng.normal(size=case["coords"].shape) * (scale * r)[:, None]
+    x = case["coords"]
+    r = np.linalg.norm(x, axis=1)
+    U = scale * (x @ rng.normal(size=(3, 3)).T) + rng.normal(size=x.shape) * (1e-3 * scale * r)[:, None]
     U[~case["movable"]] = 0
     return U
 
@@ -32,7 +35,7 @@ def _field(case, scale, seed):
 def test_fullsize_force_balance_and_derivatives(big_case, beams):
     from jointforces_b200 import _lib
     c = big_case
-    U = _field(c, 2e-2, 0)            # strains of a few percent: all three regimes of collagen12 are populated
+    U = _field(c, 1e-2, 0)            # strains of about a percent: all three regimes of collagen12 are populated
     d = _field(c, 1.0, 1)
     d /= np.abs(d).max()
     eps = 1e-6 * np.linalg.norm(c["coords"], axis=1).min()
