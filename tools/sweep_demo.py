@@ -23,7 +23,7 @@ if world > 1:
     dist.barrier()
 values = np.logspace(-1, 4, n)
 torch.cuda.synchronize(); t0 = time.time()
-table = run_sweep(mesh, base + "/out", values, jf.materials.collagen12, batch=int(os.environ.get("JF_BATCH", "16")))
+table = run_sweep(mesh, base + "/out", values, jf.materials.collagen12, batch=(int(os.environ["JF_BATCH"]) if "JF_BATCH" in os.environ else None))
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
