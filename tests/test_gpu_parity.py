@@ -340,3 +340,37 @@ def test_matches_oracle_on_structured_mesh_and_other_materials(beams):
                                            np.zeros_like(case["coords"]), mat, 0.0033, 600, 0.01, beams=beams)
         assert out["n_iter"] == ref["n_iter"]
         assert np.linalg.norm(out["U"] - ref["U"]) / np.linalg.norm(ref["U"]) < 1e-4
+
+
+def test_irregular_random_mesh_matches_oracle(beams):
+    """Unstructured input: random points, Delaunay tets of wildly varying quality and node degree (rows wider than
+    the register-resident kernel takes), arbitrary fixed/loaded node sets, non-zero prescribed displacements."""
+    from scipy.spatial import Delaunay
+    from jointforces_b200 import _lib
+    from oracle import c_oracle
+    rng = np.random.default_rng(11)
+    pts = rng.random((500, 3)) * 1e-3
+    tets = Delaunay(pts).simplices.astype(np.int32)
+    B = pts[tets[:, 1:]] - pts[tets[:, :1]]
+    vol = np.abs(np.linalg.det(B)) / 6
+    tets = tets[vol > 1e-4 * np.median(vol)]                       # drop near-degenerate hull slivers only
+    used = np.zeros(len(pts), bool); used[tets.ravel()] = True
+    assert used.all()
+    movable = pts[:, 2] > 1e-4                                         # bottom layer fixed ...
+    U0 = np.zeros_like(pts)
+    U0[~movable, 0] = 2e-6                                             # ... and sheared sideways
+    ft = np.zeros_like(pts)
+    top = pts[:, 2] > 9e-4
+    ft[top, 2] = 5e-9
+    mat = BATCH_A
+    ref = c_oracle.relax(pts, tets, movable, ft, U0, beams, mat, 0.01, 40, 0.01, nthreads=1)
+    with _lib.Context(pts, tets, movable, beams=beams) as ctx:
+        info = ctx.info()
+        ctx.set_material(*mat); ctx.set_targets(ft); ctx.set_displacements(U0)
+        relrec, cgit, n = ctx.relax(0.01, 40, 0.01)
+        U = ctx.displacements(); f = ctx.forces()
+    assert info["cg_wmax"] > 18 and info["cg_resident"] == 1          # the shared-memory resident kernel, by necessity
+    assert n[0] == ref["n_iter"]
+    assert np.array_equal(U[~movable], U0[~movable])
+    assert np.linalg.norm(U - ref["U"]) / np.linalg.norm(ref["U"]) < 1e-4
+    assert np.abs(f - ref["forces"]).max() < 1e-3 * np.abs(ref["forces"]).max()
