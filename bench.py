@@ -131,7 +131,7 @@ def hbm_regime_leg(device, peaks):
         st, info = ctx.stats(), ctx.info()
     by = cg_bytes_per_iteration(info)
     achieved = by * 50 * reps / (st["ms_cg"] * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "jf_cg_stream_kernel", "workload": "configs[4]-size icoshell mesh, %d nodes / %d tets, "
+    return {"bound": "hbm", "kernel": "jf_cg_streamhalo_kernel" if info.get("cg_stream_halo") else "jf_cg_stream_kernel", "workload": "configs[4]-size icoshell mesh, %d nodes / %d tets, "
             "collagen06; matrix %.0f MB" % (info["n_nodes"], info["n_tets"], info["n_blocks"] * 72 / 1e6),
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "us_per_cg_iteration": st["ms_cg"] * 1e3 / (50 * reps), "algorithmic_bytes_per_launch": by * 50,

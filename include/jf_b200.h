@@ -139,7 +139,8 @@ typedef struct jf_info {
     int64_t n_nodes, n_free, n_tets, n_blocks /* non-zero 3x3 blocks */, n_slots /* incl. SELL padding */;
     int32_t n_sys, n_dirs /* directions after folding */, n_beams, sm_count, cg_grid, cg_block, elem_grid, elem_block;
     int64_t bytes_device;
-    int32_t cg_resident /* 1: matrix slices live in shared memory for the whole CG solve */, cg_wmax;
+    int32_t cg_resident /* 2: matrix in registers, 1: in shared memory, for the whole CG solve; 0: streamed */, cg_wmax;
+    int32_t cg_stream_halo /* streaming kernel with per-group halo staging */, reserved;
 } jf_info;
 int jf_get_info(jf_ctx *ctx, jf_info *out);
 

@@ -568,6 +568,8 @@ extern "C" int jf_get_info(jf_ctx *c, jf_info *o) {
     o->bytes_device = c->bytes_device;
     o->cg_resident = c->cg_resident;
     o->cg_wmax = c->cg_wmax;
+    o->cg_stream_halo = c->cg_stream_halo;
+    o->reserved = 0;
     return JF_OK;
 }
 

@@ -75,9 +75,7 @@ __device__ __forceinline__ void material_eval(const MatC &m, double lam, double 
     const double dl = lam - m.ls;
     double x = neg ? lam * m.inv_d0 : dl * m.inv_ds;
     if (lin) x = 0.0;
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, x, 1.0 / 479001600.0);
-    p = fma(p, x, 1.0 / 39916800.0);
+    double p = 1.0 / 39916800.0;  // x^2/2! ... x^11/11!: truncation below 4e-18 relative for |x| < 1/8
     p = fma(p, x, 1.0 / 3628800.0);
     p = fma(p, x, 1.0 / 362880.0);
     p = fma(p, x, 1.0 / 40320.0);
@@ -104,6 +102,27 @@ __device__ __forceinline__ void material_eval(const MatC &m, double lam, double 
     }
 }
 
+// (A4) F = I + sum_m u_m (x) Phi_m
+__device__ __forceinline__ void deformation_gradient(const double *Us, const int4 nd, const double *phi, double F[3][3]) {
+    const int nn[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) F[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const double *u = Us + 3ll * nn[m];
+        const double u0 = u[0], u1 = u[1], u2 = u[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double pmj = phi[3 * m + j];
+            F[0][j] = fma(u0, pmj, F[0][j]);
+            F[1][j] = fma(u1, pmj, F[1][j]);
+            F[2][j] = fma(u2, pmj, F[2][j]);
+        }
+    }
+}
+
 template <int L>
 __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a) {
     extern __shared__ double2 tab[];
@@ -123,28 +142,14 @@ __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a
         const MatC mat(a.mat[s]);
         const int4 nd = a.tets[t];
         const double *phi = a.phi + 12 * t;
-        double P[4][3];
-#pragma unroll
-        for (int m = 0; m < 4; m++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) P[m][j] = phi[3 * m + j];
         const double *Us = a.U + (long long)s * a.N * 3;
-        const int nn[4] = {nd.x, nd.y, nd.z, nd.w};
-        // (A4) F = I + sum_m u_m (x) Phi_m
-        double F[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const double *u = Us + 3ll * nn[m];
-            const double u0 = u[0], u1 = u[1], u2 = u[2];
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                F[0][j] = fma(u0, P[m][j], F[0][j]);
-                F[1][j] = fma(u1, P[m][j], F[1][j]);
-                F[2][j] = fma(u2, P[m][j], F[2][j]);
-            }
-        }
-        // C = F^T F, off-diagonals doubled so that l^2 = sum_c C[c] * (s_j s_k)[c]
+        // C = F^T F from a deformation gradient that is NOT kept across the direction loop (it is rebuilt for the
+        // epilogue from L1-resident data: 36 FMA against 18 registers held through 43 directions)
         double C[6];
+        {
+        double F[3][3];
+        deformation_gradient(Us, nd, phi, F);
+        // off-diagonals doubled so that l^2 = sum_c C[c] * (s_j s_k)[c]
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a
                 double v = F[0][j] * F[0][k] + F[1][j] * F[1][k] + F[2][j] * F[2][k];
                 C[sym2(j, k)] = (j == k) ? v : 2.0 * v;
             }
+        }
         const double vnb = a.vol[t] / a.n_beams;
 
         double e = 0.0, G[6], H[15];
@@ -205,6 +211,9 @@ __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a
 
         const long long el = (long long)s * a.T + t;
         if (sub == 0) a.Et[el] = e;                        // (A5)
+        asm volatile("" ::: "memory");                     // make the compiler rebuild F instead of keeping it alive
+        double F[3][3];
+        deformation_gradient(Us, nd, phi, F);
 
         // (A7) f_m = Phi_m . (G F^T)
         {
