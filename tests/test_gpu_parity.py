@@ -374,3 +374,25 @@ def test_irregular_random_mesh_matches_oracle(beams):
     assert np.array_equal(U[~movable], U0[~movable])
     assert np.linalg.norm(U - ref["U"]) / np.linalg.norm(ref["U"]) < 1e-4
     assert np.abs(f - ref["forces"]).max() < 1e-3 * np.abs(ref["forces"]).max()
+
+
+def test_golden_oracle_table_rows(beams):
+    """GPU curves against the committed oracle curves of the BatchA recipe at 1 Pa .. 10 kPa (1e-3, BASELINE tolerance)."""
+    from jointforces_b200.sweep import relax_load_cases
+    from jointforces_b200.simulation import spherical_boundary_conditions, lookup_bins
+    path = os.path.join(GOLDEN, "oracle_batchA_rows.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture missing")
+    g = np.load(path)
+    case = make_case(float(g["lf_iso"]), 1.0)
+    r_in = 100 * 10 ** -6
+    bcs = [spherical_boundary_conditions(case["coords"], r_in, 10000 * 10 ** -6, float(p)) for p in g["pressure"]]
+    x, _ = lookup_bins()
+    mat = dict(zip(("K_0", "D_0", "L_S", "D_S"), g["material"]))
+    res, _ = relax_load_cases(case["coords"], case["tets"], bcs[0]["displacement"], [b["forces"] for b in bcs], mat,
+                              float(g["step"]), 600, 0.01, beams=beams, curve_bins=(r_in, x), fetch_fields=False)
+    for i, r in enumerate(res):
+        assert len(r["relrec"]) - 1 == int(g["n_iter"][i])
+        ok = ~np.isnan(g["curves"][i])
+        assert np.array_equal(np.isnan(r["curve"]), ~ok)
+        assert np.max(np.abs(r["curve"][ok] / g["curves"][i][ok] - 1)) < 1e-3, i

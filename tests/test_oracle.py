@@ -243,3 +243,29 @@ def test_oracle_reproduces_linear_table_fraction():
     ref = _golden("reference_tables.npz")
     target = _lame_fraction_of_table(ref["linear_y"][0], ref["linear_x"], 0.1, 2364.0)
     assert abs(float(g["lame_fraction"]) - target) < 0.06 * target
+
+
+def test_oracle_follows_the_shipped_batchA_table_over_four_decades_of_pressure():
+    """The strongest pin available: the reference's own saenopy output (Collagen12_BatchA.npy, recipe
+    docs/data/README.md:20-42) against the oracle on the synthetic 10,261-node mesh, at table rows 30..120
+    (1 Pa .. 1 kPa: buckling, linear and stiffening regimes; displacements spanning three decades).  Different
+    meshes => the agreement is a few per cent, not 1e-3; it corroborates the material law, the half-Hessian
+    relaxation and the stop rule at once."""
+    g = _golden("oracle_batchA_rows.npz")
+    ref = _golden("reference_tables.npz")
+    ref_rows = list(ref["rows"])
+    x = ref["x"]
+    for i, row in enumerate(g["rows"]):
+        y_ref = ref["batchA_y"][ref_rows.index(row)]
+        y = g["curves"][i]
+        ok = ~np.isnan(y) & (x > 1.2) & (x < 40)
+        ratio = y[ok] / y_ref[ok]
+        if row <= 120:
+            assert abs(np.median(ratio) - 1) < 0.06, (row, np.median(ratio))
+            assert np.all(np.abs(ratio - 1) < 0.15), (row, ratio.min(), ratio.max())
+        else:
+            # 10 kPa: a cold start stopped by the five-energy rule after 36 Newton steps is 4-22 % short of the shipped row,
+            # increasingly so in the far field -- consistent with the shipped table having been built with a working
+            # warm start (get_initial=True with an older saenopy that wrote solver.npz; SURVEY.md §0.5, Appendix B.2)
+            assert 0.75 < np.median(ratio) < 1.0
+    assert np.all(np.diff(g["curves"][:, ~np.isnan(g["curves"][0])], axis=0) > 0)
