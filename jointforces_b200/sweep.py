@@ -35,11 +35,14 @@ def shard_indices(values, rank, world):
 
 
 def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, step, max_iter, conv_crit,
-                     initial_displacements=None, device=0, batch=None, beams=None, curve_bins=None, fetch_fields=True):
+                     initial_displacements=None, device=0, batch=None, beams=None, curve_bins=None, fetch_fields=True,
+                     warm_start=False):
     """Relax every load case in ``bc_forces_list`` (same mesh, same displacement conditions) and
     return a list of dicts ``U, forces, relrec, cg_iters`` in the same order, plus the summed
     library statistics.  ``curve_bins=(r_inner, x_edges)`` adds ``curve`` (radial median curve computed on the
-    device); ``fetch_fields=False`` then skips the download of U and forces altogether."""
+    device); ``fetch_fields=False`` then skips the download of U and forces altogether.  ``warm_start=True``
+    (opt-in, one load case at a time) starts every case from the relaxed displacements of the previous one, which
+    stay on the device -- what the reference's ``get_initial`` intends (simulation.py:209-213, 227-233)."""
     from .solver import build_beams
     coords = np.ascontiguousarray(coords, dtype=np.float64)
     tets_i = np.ascontiguousarray(tets).astype(np.int32)
@@ -55,6 +58,8 @@ def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, st
     results = [None] * n
     totals = None
     contexts = {}
+    if warm_start:
+        batch = 1
     if batch:
         B = max(1, min(n, int(batch), 64))
     else:
@@ -78,7 +83,8 @@ def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, st
             ctx.reset_stats()
             for s, i in enumerate(idx):
                 ctx.set_targets(np.nan_to_num(bc_forces_list[i]), s)
-                ctx.set_displacements(U0, s)
+                if not (warm_start and a > 0):
+                    ctx.set_displacements(U0, s)
             relrec, cgit, _ = ctx.relax(step, max_iter, conv_crit)
             curves = ctx.curves() if curve_bins is not None else None
             for s, i in enumerate(idx):
@@ -96,7 +102,8 @@ def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, st
 
 
 def run_sweep(meshfile, outfolder, values, material, var_arg='pressure', max_iter=600, step=0.0033, conv_crit=0.01,
-              batch=None, callback=None, r_inner=None, r_outer=None, x0=1, x1=50, n_bins=100, write=True):
+              batch=None, callback=None, r_inner=None, r_outer=None, x0=1, x1=50, n_bins=100, write=True,
+              warm_start=False):
     """Solve ``values`` (pressures) on this rank's share, write the reference's folder layout and
     return the lookup table ``{'pressure','x','y'}`` (complete on every rank when
     ``torch.distributed`` is initialised, else this rank's rows)."""
@@ -121,7 +128,7 @@ def run_sweep(meshfile, outfolder, values, material, var_arg='pressure', max_ite
     if len(mine):
         results, stats = relax_load_cases(coords, tets, bcs[0]['displacement'], [b['forces'] for b in bcs], material, step,
                                           max_iter, conv_crit, device=device, batch=batch, curve_bins=(r_curve, x),
-                                          fetch_fields=write)
+                                          fetch_fields=write, warm_start=warm_start)
     curves = np.full((len(mine), n_bins), np.nan)
     mat_par = SemiAffineFiberMaterial(material['K_0'], material['D_0'], material['L_S'], material['D_S']).serialize()
     for j, (i, bc, res) in enumerate(zip(mine, bcs, results)):
