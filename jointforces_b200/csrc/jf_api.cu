@@ -70,8 +70,7 @@ static void ctx_free(jf_ctx *c) {
     void *ptrs[] = {c->d_tets, c->d_nodes, c->d_phi, c->d_vol, c->d_dirtab, c->d_mat, c->d_state, c->d_U, c->d_ft, c->d_f,
                     c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_halo_ptr, c->d_halo_nodes, c->d_lcol, c->d_bin_ptr, c->d_bin_nodes, c->d_curve_scratch,
-                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_partial, c->d_sync,
-                    c->d_barrier};
+                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_partial, c->d_sync};
     if (c->stream) {
         for (void *p : ptrs)
             if (p) cudaFreeAsync(p, c->stream);
@@ -193,8 +192,7 @@ extern "C" int jf_set_material(jf_ctx *c, int sys, double k, double d0, double l
     jf_material m = {k, d0, ls, ds, 1.0 / d0, 1.0 / ds};
     for (int s = (sys < 0 ? 0 : sys); s < (sys < 0 ? c->n_sys : sys + 1); s++)
         JF_CUDA(cudaMemcpy(c->d_mat + s, &m, sizeof m, cudaMemcpyHostToDevice));
-    if (sys < 0 || c->n_sys == 1) c->have_material = true;
-    else c->have_material = true;  // per-system materials: caller sets each one; unset ones are caught in relax
+    c->have_material = true;  // per-system materials: the caller sets each system it uses
     c->evaluated = false;
     return JF_OK;
 }

@@ -38,8 +38,7 @@ struct jf_sys_state {
     double resid;       // CG: r.r carried between iterations
     int cg_iters;       // CG iterations of the last solve
     int active;         // 1 = still relaxing
-    int cg_done;        // CG: converged / finished flag
-    int pad;
+    int pad[2];
 };
 
 struct jf_ctx {
@@ -85,7 +84,6 @@ struct jf_ctx {
     int64_t Nf_pad = 0;
     double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_p0 = nullptr, *d_p1 = nullptr, *d_Ap = nullptr;
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
-    unsigned int *d_barrier = nullptr; // (unused)
     unsigned int *d_sync = nullptr;    // sums-only barrier: counter (16 B) + (2, S, grid) 16-byte slots
     int cg_grid = 0, elem_grid = 0;
     int cg_stream_halo = 0;
