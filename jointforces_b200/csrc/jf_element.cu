@@ -21,6 +21,8 @@
 // split over the same lanes.  The direction table (172 x 22 doubles = 30 KB) is staged once per
 // persistent CTA in shared memory, component-major so that the lanes of a group read one
 // contiguous 16*L-byte run per LDS.128.
+#include <stdlib.h>
+
 #include "jf_internal.h"
 
 namespace {
@@ -276,14 +278,29 @@ __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a
 
 }  // namespace
 
-int jf_elem_configure(jf_ctx *c) {
-    size_t smem = (size_t)(JF_NTAB / 2) * c->n_dirs_pad * sizeof(double2);
-    JF_CUDA(cudaFuncSetAttribute(jf_element_kernel<JF_ELEM_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int L>
+static int elem_configure_t(jf_ctx *c, size_t smem) {
+    JF_CUDA(cudaFuncSetAttribute(jf_element_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_element_kernel<JF_ELEM_LANES>, JF_ELEM_BLOCK, smem));
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_element_kernel<L>, JF_ELEM_BLOCK, smem));
     if (per_sm < 1) per_sm = 1;
     c->elem_grid = c->sm_count * per_sm;
     return 0;
+}
+
+int jf_elem_configure(jf_ctx *c) {
+    size_t smem = (size_t)(JF_NTAB / 2) * c->n_dirs_pad * sizeof(double2);
+    c->elem_lanes = JF_ELEM_LANES;
+    if (const char *e = getenv("JF_ELEM_LANES")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) c->elem_lanes = v;
+    }
+    switch (c->elem_lanes) {
+        case 1: return elem_configure_t<1>(c, smem);
+        case 2: return elem_configure_t<2>(c, smem);
+        case 8: return elem_configure_t<8>(c, smem);
+        default: return elem_configure_t<4>(c, smem);
+    }
 }
 
 int jf_launch_element(jf_ctx *c) {
@@ -304,10 +321,15 @@ int jf_launch_element(jf_ctx *c) {
     a.n_dirs_pad = c->n_dirs_pad;
     a.n_beams = (double)c->n_beams;
     size_t smem = (size_t)(JF_NTAB / 2) * c->n_dirs_pad * sizeof(double2);
-    long long groups_per_block = JF_ELEM_BLOCK / JF_ELEM_LANES;
+    long long groups_per_block = JF_ELEM_BLOCK / c->elem_lanes;
     long long need = ((long long)c->n_sys * c->T + groups_per_block - 1) / groups_per_block;
     int grid = (int)(need < c->elem_grid ? (need > 0 ? need : 1) : c->elem_grid);
-    jf_element_kernel<JF_ELEM_LANES><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a);
+    switch (c->elem_lanes) {
+        case 1: jf_element_kernel<1><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        case 2: jf_element_kernel<2><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        case 8: jf_element_kernel<8><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        default: jf_element_kernel<4><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+    }
     JF_CUDA(cudaGetLastError());
     c->stats.kernel_launches++;
     return 0;

@@ -86,7 +86,7 @@ struct jf_ctx {
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
     unsigned int *d_sync = nullptr;    // sums-only barrier: counter (16 B) + (2, S, grid) 16-byte slots
     int cg_grid = 0, elem_grid = 0;
-    int cg_stream_halo = 0;
+    int cg_stream_halo = 0, elem_lanes = JF_ELEM_LANES;
     int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0, cg_hmax = 0, cg_ctas_per_sys = 0;
     int32_t *d_halo_ptr = nullptr, *d_halo_nodes = nullptr;
     // radial curve extraction (jf_curves.cu)

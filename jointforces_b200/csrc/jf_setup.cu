@@ -109,7 +109,7 @@ static int build_dirtab(jf_ctx *c, const double *beams, int n_beams) {
         wt.push_back(w);
     }
     c->n_dirs = (int)rep.size();
-    int quantum = JF_ELEM_LANES * 2;  // lanes x unroll
+    int quantum = 16;  // lanes (1, 2, 4 or 8) x unroll 2
     c->n_dirs_pad = (c->n_dirs + quantum - 1) / quantum * quantum;
     // layout: (JF_NTAB/2) planes of n_dirs_pad double2
     std::vector<double> tab((size_t)JF_NTAB * c->n_dirs_pad, 0.0);
