@@ -44,6 +44,36 @@ __global__ void bench(ulonglong2 *slots, double *partial, double *out, int iters
             grid.sync();
             if (warp == 0) { double t = 0; for (int i = lane; i < gridDim.x; i += 32) t += __ldcg(partial + (it & 1) * gridDim.x + i); t = warp_sum(t); if (lane == 0) s_tot = t; }
             __syncthreads();
+        } else if (MODE == 4) {  // last arriver fans out per-CTA flags (no polling on the counter); full fence semantics
+            epoch++;
+            __syncthreads();
+            if (warp == 0) {
+                double t = lane < nwarps ? s_warp[lane] : 0; t = warp_sum(t);
+                unsigned *ctr = (unsigned *)slots;                    // arrival counter
+                unsigned *flags = (unsigned *)slots + 64;             // one flag per CTA, 32 words apart (own 128-B line)
+                double *pp = partial + (epoch & 1) * gridDim.x;
+                unsigned last = 0;
+                if (lane == 0) {
+                    pp[blockIdx.x] = t;
+                    fence<FENCE>();
+                    unsigned old = atomicAdd(ctr, 1u);
+                    last = (old == epoch * gridDim.x - 1u);
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    for (int i = lane; i < gridDim.x; i += 32) asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(flags + 32 * i), "r"(epoch) : "memory");
+                } else if (lane == 0) {
+                    unsigned seen;
+                    do { asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + 32 * blockIdx.x) : "memory"); } while (seen != epoch);
+                }
+                __syncwarp();
+                fence<FENCE>();
+                double u = 0;
+                for (int i = lane; i < gridDim.x; i += 32) u += __ldcg(pp + i);
+                u = warp_sum(u);
+                if (lane == 0) s_tot = u;
+            }
+            __syncthreads();
         } else if (MODE == 3) {  // counter barrier that only carries the sums: no memory fences at all
             epoch++;
             __syncthreads();
@@ -110,13 +140,13 @@ __global__ void bench(ulonglong2 *slots, double *partial, double *out, int iters
 template <int MODE, int FENCE>
 float run(int grid, int block, int iters) {
     ulonglong2 *slots; double *partial, *out, *junk;
-    cudaMalloc(&slots, 2 * grid * sizeof(ulonglong2)); cudaMemset(slots, 0, 2 * grid * sizeof(ulonglong2));
+    cudaMalloc(&slots, (2 * grid + 4096) * sizeof(ulonglong2)); cudaMemset(slots, 0, (2 * grid + 4096) * sizeof(ulonglong2));
     cudaMalloc(&partial, 2 * grid * sizeof(double)); cudaMalloc(&out, 8); cudaMalloc(&junk, (size_t)grid * block * 8);
     void *args[] = {&slots, &partial, &out, &iters, &junk};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
-        cudaMemset(slots, 0, 2 * grid * sizeof(ulonglong2));
+        cudaMemset(slots, 0, (2 * grid + 4096) * sizeof(ulonglong2));
         cudaEventRecord(e0);
         cudaError_t e = cudaLaunchCooperativeKernel((void *)bench<MODE, FENCE>, dim3(grid), dim3(block), args, 0, 0);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
@@ -135,7 +165,8 @@ int main() {
         if (g * b > 148 * 2048) continue;
         printf("%5d %5d   %8.2f   %8.2f   %8.2f   %8.2f", g, b, run<0, 1>(g, b, iters), run<1, 1>(g, b, iters), run<1, 2>(g, b, iters), run<1, 0>(g, b, iters));
         printf(" | %8.2f   %8.2f   %8.2f", run<2, 1>(g, b, iters), run<2, 2>(g, b, iters), run<2, 0>(g, b, iters));
-        printf(" | counter, sums only: rel/acq %8.2f  relaxed %8.2f\n", run<3, 1>(g, b, iters), run<3, 0>(g, b, iters));
+        printf(" | counter, sums only: rel/acq %8.2f  relaxed %8.2f", run<3, 1>(g, b, iters), run<3, 0>(g, b, iters));
+        printf(" | fan-out flags: sc %8.2f acqrel %8.2f nofence %8.2f\n", run<4, 1>(g, b, iters), run<4, 2>(g, b, iters), run<4, 0>(g, b, iters));
     }
     return 0;
 }
