@@ -140,7 +140,8 @@ typedef struct jf_info {
     int32_t n_sys, n_dirs /* directions after folding */, n_beams, sm_count, cg_grid, cg_block, elem_grid, elem_block;
     int64_t bytes_device;
     int32_t cg_resident /* 2: matrix in registers, 1: in shared memory, for the whole CG solve; 0: streamed */, cg_wmax;
-    int32_t cg_stream_halo /* streaming kernel with per-group halo staging */, reserved;
+    int32_t cg_stream_halo /* streaming kernel with per-group halo staging */;
+    int32_t cg_fused /* register-resident kernel with one grid barrier per CG iteration */;
 } jf_info;
 int jf_get_info(jf_ctx *ctx, jf_info *out);
 

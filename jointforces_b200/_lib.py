@@ -46,7 +46,7 @@ class Info(C.Structure):
                 ("n_slots", C.c_int64), ("n_sys", C.c_int32), ("n_dirs", C.c_int32), ("n_beams", C.c_int32),
                 ("sm_count", C.c_int32), ("cg_grid", C.c_int32), ("cg_block", C.c_int32), ("elem_grid", C.c_int32),
                 ("elem_block", C.c_int32), ("bytes_device", C.c_int64), ("cg_resident", C.c_int32),
-                ("cg_wmax", C.c_int32), ("cg_stream_halo", C.c_int32), ("reserved", C.c_int32)]
+                ("cg_wmax", C.c_int32), ("cg_stream_halo", C.c_int32), ("cg_fused", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

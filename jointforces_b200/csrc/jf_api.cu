@@ -70,7 +70,7 @@ static void ctx_free(jf_ctx *c) {
     void *ptrs[] = {c->d_tets, c->d_nodes, c->d_phi, c->d_vol, c->d_dirtab, c->d_mat, c->d_state, c->d_U, c->d_ft, c->d_f,
                     c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_halo_ptr, c->d_halo_nodes, c->d_lcol, c->d_bin_ptr, c->d_bin_nodes, c->d_curve_scratch,
-                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_partial, c->d_sync};
+                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_r1, c->d_Ap1, c->d_partial, c->d_sync};
     if (c->stream) {
         for (void *p : ptrs)
             if (p) cudaFreeAsync(p, c->stream);
@@ -150,7 +150,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if ((rc = jf_dev_alloc(c, &c->d_Kel, S * T * 90))) break;
         if ((rc = jf_dev_alloc(c, &c->d_val, S * (size_t)c->n_slots * 9))) break;
         const size_t V = S * (size_t)c->Nf_pad * 4;
-        double **vecs[] = {&c->d_b, &c->d_x, &c->d_r, &c->d_p0, &c->d_p1, &c->d_Ap};
+        double **vecs[] = {&c->d_b, &c->d_x, &c->d_r, &c->d_p0, &c->d_p1, &c->d_Ap, &c->d_r1, &c->d_Ap1};
         for (double **v : vecs) {
             if ((rc = jf_dev_alloc(c, v, V))) break;
             if (cudaMemset(*v, 0, (V ? V : 1) * sizeof(double)) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
@@ -158,7 +158,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if (rc) break;
         if ((rc = jf_cg_configure(c))) break;
         if ((rc = jf_elem_configure(c))) break;
-        if ((rc = jf_dev_alloc(c, &c->d_partial, 4 * S * (size_t)c->cg_grid))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_partial, 8 * S * (size_t)c->cg_grid))) break;  // (2 parities, up to 3 sums, S, grid)
         if ((rc = jf_dev_alloc(c, &c->d_sync, 4 + 8 * S * (size_t)c->cg_grid))) break;  // counter + (2, S, grid) 16-byte slots
         cudaMemset(c->d_U, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_U0, 0, S * N * 3 * sizeof(double));
@@ -567,7 +567,7 @@ extern "C" int jf_get_info(jf_ctx *c, jf_info *o) {
     o->cg_resident = c->cg_resident;
     o->cg_wmax = c->cg_wmax;
     o->cg_stream_halo = c->cg_stream_halo;
-    o->reserved = 0;
+    o->cg_fused = c->cg_fused;
     return JF_OK;
 }
 

@@ -39,6 +39,8 @@ int jf_cg_resident_configure(jf_ctx *c);
 int jf_cg_resident_launch(jf_ctx *c, CgArgs &a);
 int jf_cg_stream_configure(jf_ctx *c);
 int jf_cg_stream_launch(jf_ctx *c, CgArgs &a);
+int jf_cg_fused_configure(jf_ctx *c);
+int jf_cg_fused_launch(jf_ctx *c, CgArgs &a);
 
 int jf_cg_configure(jf_ctx *c) {
     int wmax = 1;
@@ -46,7 +48,10 @@ int jf_cg_configure(jf_ctx *c) {
     c->cg_wmax = wmax;
     int rc = jf_cg_resident_configure(c);
     if (rc < 0) return rc;
-    if (rc == 1) return 0;
+    if (rc == 1) {
+        rc = jf_cg_fused_configure(c);
+        return rc < 0 ? rc : 0;
+    }
     return jf_cg_stream_configure(c);
 }
 
@@ -82,7 +87,11 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.apply_update = apply_update;
     // counter and flag words of the sums-only barrier restart at zero in every launch (a few KB, same stream)
     JF_CUDA(cudaMemsetAsync(c->d_sync, 0, 16 + (size_t)2 * c->n_sys * c->cg_grid * sizeof(ulonglong2), c->stream));
-    int rc = c->cg_resident ? jf_cg_resident_launch(c, a) : jf_cg_stream_launch(c, a);
+    // The single-reduction kernel carries r.r by recurrence; its absolute error (~4 eps times the sum of all earlier
+    // r.r) is harmless at saenopy's tolerance of 1e-5 but makes the stop test meaningless below ~1e-12, so tight
+    // tolerances go through the classic two-reduction kernels.
+    const bool fused = c->cg_fused && tol >= 1e-9;
+    int rc = fused ? jf_cg_fused_launch(c, a) : (c->cg_resident ? jf_cg_resident_launch(c, a) : jf_cg_stream_launch(c, a));
     if (rc) return rc;
     c->stats.kernel_launches++;
     c->stats.cg_launches++;

@@ -24,6 +24,7 @@ struct CgArgs {
     const double *val;
     const double *b;
     double *x, *r, *p0, *p1, *Ap;
+    double *r1, *Ap1;  // second generation of r and Ap (single-reduction kernel)
     double *partial;  // (2, n_sys, grid) per-CTA partial sums, double-buffered by barrier parity
     int sums_only;          // 1: p.Ap reduction through the fence-free sums-only barrier
     unsigned *sync_ctr;     // arrival counter of the sums-only barrier (zeroed before every launch)

@@ -1,0 +1,327 @@
+// Register-resident CG with ONE grid barrier per iteration (see jf_cg.cu for the CG overview and
+// jf_cg_resident.cu for the data placement this kernel shares with jf_cg_regres_kernel).
+//
+// Classic Hestenes-Stiefel needs two global reductions per iteration: p.Ap (for alpha) and r.r of the
+// updated residual (for beta and the stop test).  The second one is algebraically available at the
+// time of the first:
+//       r' = r - alpha Ap      =>      r'.r' = r.r - 2 alpha (r.Ap) + alpha^2 (Ap.Ap)
+// so one all-reduce of (p.Ap, r.Ap, Ap.Ap) yields alpha, the new r.r, the stop decision and beta.
+// The iterates are the same as saenopy's cg in exact arithmetic (same alpha, same beta, same stop
+// quantity); in floating point r'.r' carries a relative error of ~3 eps * (r.r)/(r'.r'), i.e. 1e-15
+// for CG's usual 0.5-1.0 reduction per step -- the size of the summation-order differences between
+// any two implementations of the dot product (DESIGN.md "Trajectory sensitivity").
+//
+// The vector updates that depended on the second barrier are deferred into the next iteration and
+// formed on the fly where they are needed:
+//   own row (registers):  x += alpha_prev p;  r -= alpha_prev Ap;  p = r + beta_prev p
+//   halo node j (once per distinct neighbour; every CTA keeps r_j and p_j of ITS halo nodes in shared
+//   memory for the whole solve and advances them itself):
+//                          r_j -= alpha_prev Ap_j;  p_j = r_j + beta_prev p_j
+// with the same FMA forms on the same inputs, so an owner's registers and its neighbours' halo copies
+// agree bit for bit.  The only vector that crosses CTAs is therefore Ap: one 32-byte store per row and
+// one 256-bit load per halo node per iteration; two generations alternate by parity.
+//
+// Measured on config 2: 6.4-6.8 us per iteration with two barriers -> see DESIGN.md / profiles.
+#include <stdlib.h>
+
+#include "jf_cg_common.cuh"
+
+namespace {
+
+constexpr int F_J = 9;          // block columns per lane half
+constexpr int F_HALO_BATCH = 2;
+constexpr int F_MAX_SYS = 16;   // systems per launch in this kernel (shared tables are sized by it)
+
+struct FusedShared {
+    double warp[3][F_MAX_SYS][8];  // per-warp partials of (p.Ap, r.Ap, Ap.Ap)
+    double normb[F_MAX_SYS], rho[F_MAX_SYS], alpha[F_MAX_SYS], beta[F_MAX_SYS], tot0[F_MAX_SYS];
+    int done[F_MAX_SYS], iters[F_MAX_SYS];
+};
+
+// all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order.
+// After it the lane that owns system s's totals runs `update(s, t0, t1, t2)` before the CTA barrier.
+template <int NQ, typename F>
+__device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, F update) {
+    epoch++;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double *part = a.partial + (size_t)(epoch & 1u) * 3 * a.n_sys * gridDim.x;
+    __syncthreads();
+    for (int v = warp; v < NQ * a.n_sys; v += nwarps) {
+        const int q = v / a.n_sys, s = v - q * a.n_sys;
+        double x = lane < nwarps ? sh.warp[q][s][lane] : 0.0;
+        x = warp_sum(x);
+        if (lane == 0) part[(size_t)v * gridDim.x + blockIdx.x] = x;
+    }
+    grid.sync();
+    for (int s = warp; s < a.n_sys; s += nwarps) {
+        // all loads of all sums in flight before the first shuffle (grid <= 160 CTAs: five per lane and sum)
+        double v[3][5];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const double *p = part + (size_t)(q * a.n_sys + s) * gridDim.x;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int i = lane + 32 * k;
+                v[q][k] = i < (int)gridDim.x ? __ldcg(p + i) : 0.0;
+            }
+        }
+        double t[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < NQ; q++) t[q] = warp_sum((((v[q][0] + v[q][1]) + v[q][2]) + v[q][3]) + v[q][4]);
+        if (lane == 0) update(s, t[0], t[1], t[2]);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ FusedShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = blockDim.x >> 6;  // slices per CTA (two warps per 32-row slice)
+    const int s = blockIdx.x / a.ctas_per_sys;
+    const int cb = blockIdx.x - s * a.ctas_per_sys;
+    const int half = lane >> 4;
+    const int rloc = warp * 16 + (lane & 15);
+    const long long sl = (long long)cb * W + (rloc >> 5);
+    const bool have = sl < a.n_slices;
+    const bool owner = have && half == 0;
+    const long long row = sl * 32 + (rloc & 31);
+    const long long vstride = a.Nf_pad * 4;
+    double *hr = (double *)dyn_smem;             // hmax * 3: r of every halo node, advanced locally each iteration
+    double *hp = hr + (size_t)a.hmax * 3;        // hmax * 3: p of every halo node
+    int *hn = (int *)(hp + (size_t)a.hmax * 3);  // hmax
+    const int h0 = a.halo_ptr[cb], nh = a.halo_ptr[cb + 1] - h0;
+    unsigned epoch = 0;
+
+    if (threadIdx.x < a.n_sys) {
+        sh.done[threadIdx.x] = a.state[threadIdx.x].active ? 0 : 1;
+        sh.iters[threadIdx.x] = 0;
+        sh.alpha[threadIdx.x] = 0.0;
+        sh.beta[threadIdx.x] = 0.0;
+    }
+    for (int i = threadIdx.x; i < 3 * F_MAX_SYS * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
+    __syncthreads();
+    const bool sys_on = !sh.done[s];
+
+    // the row's blocks and local column indices, once, into registers
+    double m[F_J][9];
+    int lc[F_J];
+    int w = 0;
+#pragma unroll
+    for (int jj = 0; jj < F_J; jj++) {
+        lc[jj] = 0;
+#pragma unroll
+        for (int q = 0; q < 9; q++) m[jj][q] = 0.0;
+    }
+    if (have && sys_on) {
+        const int q0 = a.slice_ptr[sl];
+        w = (a.slice_ptr[sl + 1] - q0) >> 5;
+        const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288 + (rloc & 31);
+#pragma unroll
+        for (int jj = 0; jj < F_J; jj++) {
+            const int j = 2 * jj + half;
+            if (j < w) {
+                lc[jj] = a.lcol[q0 + j * 32 + (rloc & 31)];
+#pragma unroll
+                for (int q = 0; q < 9; q++) m[jj][q] = v[288 * j + 32 * q];
+            }
+        }
+    }
+    for (int h = threadIdx.x; h < nh; h += blockDim.x) hn[h] = a.halo_nodes[h0 + h];
+    __syncthreads();
+
+    // the only vector that travels between CTAs: Ap of the iteration, two generations
+    double4 *const A_0 = (double4 *)(a.Ap + s * vstride), *const A_1 = (double4 *)(a.Ap1 + s * vstride);
+    // r_0 = b and p = 0 for this CTA's halo nodes
+    if (sys_on) {
+        const double4 *b4 = (const double4 *)(a.b + s * vstride);
+        for (int h = threadIdx.x; h < nh; h += blockDim.x) {
+            const double4 bv = b4[hn[h]];
+            hr[3 * h] = bv.x; hr[3 * h + 1] = bv.y; hr[3 * h + 2] = bv.z;
+            hp[3 * h] = 0.0; hp[3 * h + 1] = 0.0; hp[3 * h + 2] = 0.0;
+        }
+    }
+    double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, y0 = 0, y1 = 0, y2 = 0;
+    double acc = 0.0;
+    if (have && sys_on) {
+        const double4 bv = ((const double4 *)(a.b + s * vstride))[row];
+        r0 = bv.x; r1 = bv.y; r2 = bv.z;
+        if (owner) {
+            A_1[row] = make_double4(0.0, 0.0, 0.0, 0.0);  // generation "-1": Ap = 0 makes iteration 0 the general case (alpha = beta = 0)
+            acc = r0 * r0 + r1 * r1 + r2 * r2;
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.warp[0][s][warp] = acc;
+    fused_allreduce<1>(a, grid, sh, epoch, [&](int ss, double t0, double, double) {
+        sh.normb[ss] = t0;
+        sh.rho[ss] = t0;
+        sh.tot0[ss] = t0;
+        if (!sh.done[ss] && t0 == 0.0) sh.done[ss] = 1;  // cg returns 0 when normb == 0
+    });
+
+#ifdef JF_CG_TIMING
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
+    int cur = 0;
+    for (long long it = 1; it <= a.maxiter; it++) {
+        int all = 1;
+        for (int q = 0; q < a.n_sys; q++) all &= sh.done[q];
+        if (all) break;
+        TMARK(0);
+        const bool on = !sh.done[s];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        if (on) {
+            const double alpha = sh.alpha[s], beta = sh.beta[s];  // of the previous iteration (0, 0 for the first)
+            const double4 *Ao = cur ? A_0 : A_1;  // Ap of the previous iteration
+            double4 *An = cur ? A_1 : A_0;        // this iteration's
+            // ---- halo: r_j -= alpha Ap_j ; p_j = r_j + beta p_j, once per distinct block column, r and p kept here ----
+            for (int hb = threadIdx.x; hb < nh; hb += F_HALO_BATCH * blockDim.x) {
+                double4 av[F_HALO_BATCH];
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++) {
+                    const int h = hb + k * blockDim.x;
+                    av[k] = ld_node(Ao + hn[h < nh ? h : hb]);
+                }
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++) {
+                    const int h = hb + k * blockDim.x;
+                    if (h < nh) {
+                        const double rx = fma(-alpha, av[k].x, hr[3 * h]), ry = fma(-alpha, av[k].y, hr[3 * h + 1]),
+                                     rz = fma(-alpha, av[k].z, hr[3 * h + 2]);
+                        hr[3 * h] = rx; hr[3 * h + 1] = ry; hr[3 * h + 2] = rz;
+                        hp[3 * h] = fma(beta, hp[3 * h], rx);
+                        hp[3 * h + 1] = fma(beta, hp[3 * h + 1], ry);
+                        hp[3 * h + 2] = fma(beta, hp[3 * h + 2], rz);
+                    }
+                }
+            }
+            // ---- own row: the deferred updates of the previous iteration ------------------------------------
+            if (have) {
+                x0 = fma(alpha, p0, x0);
+                x1 = fma(alpha, p1, x1);
+                x2 = fma(alpha, p2, x2);
+                r0 = fma(-alpha, y0, r0);
+                r1 = fma(-alpha, y1, r1);
+                r2 = fma(-alpha, y2, r2);
+                p0 = fma(beta, p0, r0);
+                p1 = fma(beta, p1, r1);
+                p2 = fma(beta, p2, r2);
+            }
+            __syncthreads();
+            // ---- block row: Ap_i = sum_j K_ij p_j ----------------------------------------------------------------
+            if (have) {
+                y0 = y1 = y2 = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < F_J; jj++) {
+                    if (2 * jj < w) {
+                        const double *pj = hp + 3 * lc[jj];
+                        const double px = pj[0], py = pj[1], pz = pj[2];
+                        JF_BLOCK_FMA(m[jj], 1, px, py, pz)
+                    }
+                }
+                y0 += __shfl_xor_sync(0xffffffffu, y0, 16);
+                y1 += __shfl_xor_sync(0xffffffffu, y1, 16);
+                y2 += __shfl_xor_sync(0xffffffffu, y2, 16);
+                if (owner) {
+                    An[row] = make_double4(y0, y1, y2, 0.0);
+                    a0 = p0 * y0 + p1 * y1 + p2 * y2;
+                    a1 = r0 * y0 + r1 * y1 + r2 * y2;
+                    a2 = y0 * y0 + y1 * y1 + y2 * y2;
+                }
+            }
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) {
+            sh.warp[0][s][warp] = a0;
+            sh.warp[1][s][warp] = a1;
+            sh.warp[2][s][warp] = a2;
+        }
+        TMARK(1);
+        fused_allreduce<3>(a, grid, sh, epoch, [&](int ss, double pAp, double rAp, double ApAp) {
+            if (sh.done[ss]) return;
+            const double rho = sh.rho[ss];
+            const double alpha = rho / pAp;
+            const double rsnew = fma(alpha * alpha, ApAp, fma(-2.0 * alpha, rAp, rho));  // r'.r' without a second pass
+            sh.alpha[ss] = alpha;
+            sh.iters[ss] = (int)it;
+            if (rsnew < a.tol * sh.normb[ss] || it == a.maxiter || !(rsnew > 0.0)) {
+                sh.done[ss] = 1;  // the pending x += alpha p is applied after the loop
+            } else {
+                sh.beta[ss] = rsnew / rho;
+                sh.rho[ss] = rsnew;
+            }
+        });
+        TMARK(2);
+        cur ^= 1;
+    }
+#ifdef JF_CG_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("cg-fused iters %d cycles/iter: top %.0f phaseA %.0f allreduce %.0f  (nh %d)\n", sh.iters[0], (double)tacc[0] / sh.iters[0],
+               (double)tacc[1] / sh.iters[0], (double)tacc[2] / sh.iters[0], nh);
+#endif
+
+    // the last iteration's x += alpha p, then (A12) U[free] += step * x ; du = step^2 * sum x^2
+    acc = 0.0;
+    if (have && a.state[s].active) {
+        const double alpha = sh.alpha[s];
+        x0 = fma(alpha, p0, x0);
+        x1 = fma(alpha, p1, x1);
+        x2 = fma(alpha, p2, x2);
+        if (owner) {
+            ((double4 *)(a.x + s * vstride))[row] = make_double4(x0, x1, x2, 0.0);
+            if (a.apply_update && row < a.Nf) {
+                double *U = a.U + ((long long)s * a.N + row) * 3;
+                U[0] += a.step * x0;
+                U[1] += a.step * x1;
+                U[2] += a.step * x2;
+                acc = x0 * x0 + x1 * x1 + x2 * x2;
+            }
+        }
+    }
+    if (a.apply_update) {
+        acc = warp_sum(acc);
+        if (lane == 0) sh.warp[0][s][warp] = acc;
+        fused_allreduce<1>(a, grid, sh, epoch, [&](int ss, double t0, double, double) { sh.tot0[ss] = t0; });
+    }
+    if (blockIdx.x == 0 && threadIdx.x < a.n_sys && a.state[threadIdx.x].active) {
+        const int q = threadIdx.x;
+        a.state[q].cg_iters = sh.iters[q];
+        a.state[q].normb = sh.normb[q];
+        a.state[q].resid = sh.rho[q];
+        if (a.apply_update) a.state[q].du = a.step * a.step * sh.tot0[q];
+    }
+}
+
+}  // namespace
+
+// usable when the register-resident layout applies (decided by jf_cg_resident_configure: cg_resident == 2)
+int jf_cg_fused_configure(jf_ctx *c) {
+    c->cg_fused = 0;
+    if (c->cg_resident != 2 || c->n_sys > F_MAX_SYS || getenv("JF_CG_CLASSIC")) return 0;
+    const size_t smem = (size_t)c->cg_hmax * (6 * sizeof(double) + sizeof(int));
+    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_kernel, c->cg_res_warps * 64, smem));
+    if (per_sm < 1) return 0;
+    c->cg_fused_smem = smem;
+    c->cg_fused = 1;
+    return 1;
+}
+
+int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
+    a.halo_ptr = c->d_halo_ptr;
+    a.halo_nodes = c->d_halo_nodes;
+    a.lcol = c->d_lcol;
+    a.hmax = c->cg_hmax;
+    a.ctas_per_sys = c->cg_ctas_per_sys;
+    a.r1 = c->d_r1;
+    a.Ap1 = c->d_Ap1;
+    void *args[] = {&a};
+    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_fused_kernel, dim3(c->cg_grid), dim3(c->cg_res_warps * 64), args, c->cg_fused_smem,
+                                        c->stream));
+    return 0;
+}

@@ -229,23 +229,26 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
     from jointforces_b200 import _lib
     c = make_case(0.3, 100.0)
     res = []
-    for flags, no_regres in ((0, False), (0, True), (_lib.JF_FLAG_NO_RESIDENT, False)):
-        if no_regres:
-            monkeypatch.setenv("JF_CG_NO_REGRES", "1")
-        else:
-            monkeypatch.delenv("JF_CG_NO_REGRES", raising=False)
+    for flags, no_regres, classic in ((0, False, False), (0, False, True), (0, True, True), (_lib.JF_FLAG_NO_RESIDENT, False, True)):
+        for name, on in (("JF_CG_NO_REGRES", no_regres), ("JF_CG_CLASSIC", classic)):
+            if on:
+                monkeypatch.setenv(name, "1")
+            else:
+                monkeypatch.delenv(name, raising=False)
         with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams, flags=flags) as ctx:
             ctx.set_material(*COLLAGEN12)
             ctx.set_targets(c["f_target"])
             ctx.set_displacements(np.zeros_like(c["coords"]))
             relrec, cgit, n = ctx.relax(0.0033, 25, 0.01)
-            res.append((ctx.displacements(), cgit[0], ctx.info()["cg_resident"]))
+            info = ctx.info()
+            res.append((ctx.displacements(), cgit[0], (info["cg_resident"], info["cg_fused"])))
     kinds = [r[2] for r in res]
-    assert kinds[0] in (1, 2) and kinds[1] == 1 and kinds[2] == 0, kinds   # 2 needs rows <= 18 blocks wide
-    for other in res[:2]:
+    # single-reduction register kernel / classic register kernel / classic shared-memory kernel / classic streaming kernel
+    assert kinds == [(2, 1), (2, 0), (1, 0), (0, 0)], kinds
+    for other in res[:3]:
         # CG's loose stop makes the iteration count rounding-sensitive (DESIGN.md "Trajectory sensitivity")
-        assert np.abs(other[1].astype(int) - res[2][1]).max() <= 0.05 * res[2][1].max()
-        assert np.linalg.norm(other[0] - res[2][0]) / np.linalg.norm(res[2][0]) < 5e-5
+        assert np.abs(other[1].astype(int) - res[3][1]).max() <= 0.05 * res[3][1].max()
+        assert np.linalg.norm(other[0] - res[3][0]) / np.linalg.norm(res[3][0]) < 5e-5
 
 
 def test_resident_batch_of_two_systems(beams):
