@@ -116,9 +116,8 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
     c->flags = flags;
     int rc = 0;
     do {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "props", __FILE__, __LINE__); break; }
-        c->sm_count = prop.multiProcessorCount;
+        // single attributes, not cudaGetDeviceProperties: the full property query costs 100-350 ms now and then
+        if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "attr", __FILE__, __LINE__); break; }
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (!coop) { jf_set_error("device lacks cooperative launch"); rc = JF_ERR_CUDA; break; }
@@ -133,7 +132,9 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
         }
+        StageTimer tm;
         if ((rc = jf_build_structure(c, nodes, tets, movable, beams, n_beams))) break;
+        tm.mark("(structure total)");
         const size_t S = (size_t)n_sys, N = (size_t)c->N, T = (size_t)c->T;
         // (blocking cudaMemcpy/cudaMemset below run on the legacy stream; c->stream is non-blocking,
         //  so every batch of stream-ordered allocations is followed by a stream synchronize)
@@ -156,7 +157,9 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
             if (cudaMemset(*v, 0, (V ? V : 1) * sizeof(double)) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
         }
         if (rc) break;
+        tm.mark("allocations+memsets");
         if ((rc = jf_cg_configure(c))) break;
+        tm.mark("cg configure");
         if ((rc = jf_elem_configure(c))) break;
         if ((rc = jf_dev_alloc(c, &c->d_partial, 8 * S * (size_t)c->cg_grid))) break;  // (2 parities, up to 3 sums, S, grid)
         if ((rc = jf_dev_alloc(c, &c->d_sync, 4 + 8 * S * (size_t)c->cg_grid))) break;  // counter + (2, S, grid) 16-byte slots
@@ -168,7 +171,9 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         for (size_t s = 0; s < S; s++) c->h_state[s].active = 1;
         if (cudaMemcpy(c->d_state, c->h_state, S * sizeof(jf_sys_state), cudaMemcpyHostToDevice) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "state", __FILE__, __LINE__); break; }
         c->have_targets.assign(S, 0);
+        tm.mark("elem configure+state");
         if (cudaDeviceSynchronize() != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__); break; }
+        tm.mark("device synchronize");
     } while (0);
     if (rc) {
         ctx_free(c);

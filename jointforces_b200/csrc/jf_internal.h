@@ -16,6 +16,24 @@
 #define JF_ELEM_BLOCK 128
 #define JF_CG_BLOCK 512
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
+
+// JF_TIMING=1 in the environment prints the host-side setup stages to stderr
+struct StageTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    StageTimer() : on(getenv("JF_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[jf setup] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 void jf_set_error(const char *fmt, ...);
 int jf_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 #define JF_CUDA(x)                                                              \

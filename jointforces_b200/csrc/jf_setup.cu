@@ -17,19 +17,6 @@
 
 #include "jf_internal.h"
 
-// JF_TIMING=1 in the environment prints the host-side setup stages to stderr
-struct StageTimer {
-    bool on;
-    std::chrono::steady_clock::time_point t;
-    StageTimer() : on(getenv("JF_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
-    void mark(const char *what) {
-        if (!on) return;
-        auto n = std::chrono::steady_clock::now();
-        fprintf(stderr, "[jf setup] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
-        t = n;
-    }
-};
-
 // split [0,n) over host threads (structure build only; results do not depend on the thread count)
 template <typename F>
 static void parallel_for(int64_t n, F fn) {
