@@ -29,7 +29,7 @@
 namespace {
 
 constexpr int F_J = 9;          // block columns per lane half
-constexpr int F_HALO_BATCH = 2;
+constexpr int F_HALO_BATCH = 3;  // one round of loads covers 768 halo nodes (config 2: 282-562 per CTA)
 constexpr int F_MAX_SYS = 16;   // systems per launch in this kernel (shared tables are sized by it)
 
 struct FusedShared {
