@@ -100,3 +100,21 @@ def test_device_curves_equal_host_formula_bitwise(beams):
         assert (~np.isnan(expect)).sum() > 40
         assert np.array_equal(np.isnan(got[s]), np.isnan(expect))
         assert np.array_equal(got[s][~np.isnan(expect)], expect[~np.isnan(expect)])
+
+
+def test_opt_in_warm_start_chains_load_cases(beams):
+    """warm_start=True: every load case starts from the previous one's relaxed field (kept on the device); the
+    default stays the reference's effective behaviour, a cold start per pressure."""
+    from jointforces_b200.sweep import relax_load_cases
+    from jointforces_b200.mesh import generate_spherical_inclusion
+    coords, tets = generate_spherical_inclusion(lf_iso=0.667)
+    bcs = [jf.simulation.spherical_boundary_conditions(coords, 1e-4, 1e-2, p) for p in (50.0, 55.0, 60.0)]
+    args = (coords, tets, bcs[0]["displacement"], [b["forces"] for b in bcs], jf.materials.collagen12, 0.0033, 600, 0.01)
+    cold, _ = relax_load_cases(*args, beams=beams)
+    warm, _ = relax_load_cases(*args, beams=beams, warm_start=True)
+    n_cold = [len(r["relrec"]) - 1 for r in cold]
+    n_warm = [len(r["relrec"]) - 1 for r in warm]
+    assert n_warm[0] == n_cold[0] and np.array_equal(warm[0]["U"], cold[0]["U"])     # the first case has nothing to start from
+    assert all(w < c / 2 for w, c in zip(n_warm[1:], n_cold[1:]))                     # later ones stop after a few steps
+    for w, c in zip(warm[1:], cold[1:]):                                              # at nearly the same early-stopped field
+        assert np.linalg.norm(w["U"] - c["U"]) < 0.1 * np.linalg.norm(c["U"])
