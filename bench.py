@@ -325,7 +325,8 @@ def main():
             "wall_ms_per_step": wall * 1e3 / K,
         },
         "roofline": {"bound": "hbm", "kernel": "jf_cg_fused_kernel" if info.get("cg_fused") else "jf_cg_regres_kernel" if info["cg_resident"] == 2 else
-                     ("jf_cg_resident_kernel" if info["cg_resident"] == 1 else "jf_cg_stream_kernel"), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     ("jf_cg_resident_kernel" if info["cg_resident"] == 1 else
+                      ("jf_cg_streamhalo_kernel" if info.get("cg_stream_halo") else "jf_cg_stream_kernel")), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": "of " + peak_kind,
                      "algorithmic_bytes_per_launch": by_iter * cg_iters / max(1, st["cg_launches"]),
                      "note": ("matrix %.0f MB %s the 126 MB L2; " % (matrix_mb, "fits in" if matrix_mb < 100 else "exceeds")) +
