@@ -30,6 +30,9 @@ namespace {
 
 constexpr int F_J = 9;          // block columns per lane half
 constexpr int F_HALO_BATCH = 3;  // one round of loads covers 768 halo nodes (config 2: 282-562 per CTA)
+#ifndef F_REPLICAS
+#define F_REPLICAS 4
+#endif
 constexpr int F_MAX_SYS = 16;   // systems per launch in this kernel (shared tables are sized by it)
 
 struct FusedShared {
@@ -44,13 +47,15 @@ template <int NQ, typename F>
 __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, F update) {
     epoch++;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    double *part = a.partial + (size_t)(epoch & 1u) * 3 * a.n_sys * gridDim.x;
+    // F_REPLICAS copies of the partial table: CTA b reads copy b % F_REPLICAS, so a line has fewer simultaneous readers
+    const size_t table = (size_t)3 * a.n_sys * gridDim.x;
+    double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
     __syncthreads();
     for (int v = warp; v < NQ * a.n_sys; v += nwarps) {
         const int q = v / a.n_sys, s = v - q * a.n_sys;
         double x = lane < nwarps ? sh.warp[q][s][lane] : 0.0;
         x = warp_sum(x);
-        if (lane == 0) part[(size_t)v * gridDim.x + blockIdx.x] = x;
+        if (lane < F_REPLICAS) part[lane * table + (size_t)v * gridDim.x + blockIdx.x] = x;
     }
     grid.sync();
     for (int s = warp; s < a.n_sys; s += nwarps) {
@@ -58,7 +63,7 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
         double v[3][5];
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-            const double *p = part + (size_t)(q * a.n_sys + s) * gridDim.x;
+            const double *p = part + (blockIdx.x % F_REPLICAS) * table + (size_t)(q * a.n_sys + s) * gridDim.x;
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const int i = lane + 32 * k;
