@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
 // usable when the register-resident layout applies (decided by jf_cg_resident_configure: cg_resident == 2)
 int jf_cg_fused_configure(jf_ctx *c) {
     c->cg_fused = 0;
-    if (c->cg_resident != 2 || c->n_sys > F_MAX_SYS || getenv("JF_CG_CLASSIC")) return 0;
+    // the collect keeps five partial sums per lane in registers: at most 160 CTAs (B200: 148 SMs)
+    if (c->cg_resident != 2 || c->n_sys > F_MAX_SYS || c->cg_grid > 160 || getenv("JF_CG_CLASSIC")) return 0;
     const size_t smem = (size_t)c->cg_hmax * (6 * sizeof(double) + sizeof(int));
     JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
