@@ -161,7 +161,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if ((rc = jf_cg_configure(c))) break;
         tm.mark("cg configure");
         if ((rc = jf_elem_configure(c))) break;
-        if ((rc = jf_dev_alloc(c, &c->d_partial, 64 * S * (size_t)c->cg_grid))) break;  // (2 parities, <= 8 replicas, <= 3 sums, S, grid)
+        if ((rc = jf_dev_alloc(c, &c->d_partial, 64 * S * (size_t)std::max(c->cg_grid, c->cg_fused_stream_grid)))) break;  // (2 parities, <= 8 replicas, <= 3 sums, S, grid)
         if ((rc = jf_dev_alloc(c, &c->d_sync, 4 + 8 * S * (size_t)c->cg_grid))) break;  // counter + (2, S, grid) 16-byte slots
         cudaMemset(c->d_U, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_U0, 0, S * N * 3 * sizeof(double));
@@ -572,7 +572,7 @@ extern "C" int jf_get_info(jf_ctx *c, jf_info *o) {
     o->cg_resident = c->cg_resident;
     o->cg_wmax = c->cg_wmax;
     o->cg_stream_halo = c->cg_stream_halo;
-    o->cg_fused = c->cg_fused;
+    o->cg_fused = c->cg_fused + 2 * c->cg_fused_stream;  // 1: register-resident, 2: streaming single-reduction kernel
     return JF_OK;
 }
 

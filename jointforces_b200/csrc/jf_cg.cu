@@ -41,6 +41,8 @@ int jf_cg_stream_configure(jf_ctx *c);
 int jf_cg_stream_launch(jf_ctx *c, CgArgs &a);
 int jf_cg_fused_configure(jf_ctx *c);
 int jf_cg_fused_launch(jf_ctx *c, CgArgs &a);
+int jf_cg_fused_stream_configure(jf_ctx *c);
+int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a);
 
 int jf_cg_configure(jf_ctx *c) {
     int wmax = 1;
@@ -52,7 +54,10 @@ int jf_cg_configure(jf_ctx *c) {
         rc = jf_cg_fused_configure(c);
         return rc < 0 ? rc : 0;
     }
-    return jf_cg_stream_configure(c);
+    rc = jf_cg_stream_configure(c);
+    if (rc) return rc;
+    rc = jf_cg_fused_stream_configure(c);
+    return rc < 0 ? rc : 0;
 }
 
 int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_update) {
@@ -91,7 +96,10 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     // r.r) is harmless at saenopy's tolerance of 1e-5 but makes the stop test meaningless below ~1e-12, so tight
     // tolerances go through the classic two-reduction kernels.
     const bool fused = c->cg_fused && tol >= 1e-9;
-    int rc = fused ? jf_cg_fused_launch(c, a) : (c->cg_resident ? jf_cg_resident_launch(c, a) : jf_cg_stream_launch(c, a));
+    const bool fused_stream = c->cg_fused_stream && tol >= 1e-9;
+    int rc = fused ? jf_cg_fused_launch(c, a)
+                   : (c->cg_resident ? jf_cg_resident_launch(c, a)
+                                     : (fused_stream ? jf_cg_fused_stream_launch(c, a) : jf_cg_stream_launch(c, a)));
     if (rc) return rc;
     c->stats.kernel_launches++;
     c->stats.cg_launches++;

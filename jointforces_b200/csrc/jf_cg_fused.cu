@@ -24,6 +24,8 @@
 // Measured on config 2: 6.4-6.8 us per iteration with two barriers -> see DESIGN.md / profiles.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "jf_cg_common.cuh"
 
 namespace {
@@ -38,12 +40,12 @@ constexpr int F_MAX_SYS = 16;   // systems per launch in this kernel (shared tab
 struct FusedShared {
     double warp[3][F_MAX_SYS][8];  // per-warp partials of (p.Ap, r.Ap, Ap.Ap)
     double normb[F_MAX_SYS], rho[F_MAX_SYS], alpha[F_MAX_SYS], beta[F_MAX_SYS], tot0[F_MAX_SYS];
-    int done[F_MAX_SYS], iters[F_MAX_SYS];
+    int done[F_MAX_SYS], iters[F_MAX_SYS], lastcur[F_MAX_SYS];
 };
 
 // all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order.
 // After it the lane that owns system s's totals runs `update(s, t0, t1, t2)` before the CTA barrier.
-template <int NQ, typename F>
+template <int NQ, int KMAX, typename F>
 __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, F update) {
     epoch++;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -59,20 +61,25 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
     }
     grid.sync();
     for (int s = warp; s < a.n_sys; s += nwarps) {
-        // all loads of all sums in flight before the first shuffle (grid <= 160 CTAs: five per lane and sum)
-        double v[3][5];
+        // all loads of all sums in flight before the first shuffle (grid <= 32*KMAX CTAs: KMAX per lane and sum)
+        double v[3][KMAX];
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             const double *p = part + (blockIdx.x % F_REPLICAS) * table + (size_t)(q * a.n_sys + s) * gridDim.x;
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
+            for (int k = 0; k < KMAX; k++) {
                 const int i = lane + 32 * k;
                 v[q][k] = i < (int)gridDim.x ? __ldcg(p + i) : 0.0;
             }
         }
         double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int q = 0; q < NQ; q++) t[q] = warp_sum((((v[q][0] + v[q][1]) + v[q][2]) + v[q][3]) + v[q][4]);
+        for (int q = 0; q < NQ; q++) {
+            double x = v[q][0];
+#pragma unroll
+            for (int k = 1; k < KMAX; k++) x += v[q][k];
+            t[q] = warp_sum(x);
+        }
         if (lane == 0) update(s, t[0], t[1], t[2]);
     }
     __syncthreads();
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     }
     acc = warp_sum(acc);
     if (lane == 0) sh.warp[0][s][warp] = acc;
-    fused_allreduce<1>(a, grid, sh, epoch, [&](int ss, double t0, double, double) {
+    fused_allreduce<1, 5>(a, grid, sh, epoch, [&](int ss, double t0, double, double) {
         sh.normb[ss] = t0;
         sh.rho[ss] = t0;
         sh.tot0[ss] = t0;
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             sh.warp[2][s][warp] = a2;
         }
         TMARK(1);
-        fused_allreduce<3>(a, grid, sh, epoch, [&](int ss, double pAp, double rAp, double ApAp) {
+        fused_allreduce<3, 5>(a, grid, sh, epoch, [&](int ss, double pAp, double rAp, double ApAp) {
             if (sh.done[ss]) return;
             const double rho = sh.rho[ss];
             const double alpha = rho / pAp;
@@ -290,8 +297,220 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     if (a.apply_update) {
         acc = warp_sum(acc);
         if (lane == 0) sh.warp[0][s][warp] = acc;
-        fused_allreduce<1>(a, grid, sh, epoch, [&](int ss, double t0, double, double) { sh.tot0[ss] = t0; });
+        fused_allreduce<1, 5>(a, grid, sh, epoch, [&](int ss, double t0, double, double) { sh.tot0[ss] = t0; });
     }
+    if (blockIdx.x == 0 && threadIdx.x < a.n_sys && a.state[threadIdx.x].active) {
+        const int q = threadIdx.x;
+        a.state[q].cg_iters = sh.iters[q];
+        a.state[q].normb = sh.normb[q];
+        a.state[q].resid = sh.rho[q];
+        if (a.apply_update) a.state[q].du = a.step * a.step * sh.tot0[q];
+    }
+}
+
+// =================================================================================================
+// Single-reduction CG for matrices that are streamed (mid-size meshes, lockstep batches): same algebra as
+// above, vectors in global memory.  Groups of FS_SLICES slices; per group the halo p_j = (R_j - alpha AP_j) +
+// beta P_j is formed once per distinct node from the previous generation's published (r, Ap, p) and kept in
+// shared memory for the group's block-row products; the owner pass advances x, r, p of its rows and publishes
+// the new generation.  One grid barrier per iteration instead of two and no separate vector-update pass.
+// =================================================================================================
+constexpr int FS_SLICES = 8;
+constexpr int FS_THREADS = FS_SLICES * 32;
+
+__global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double hv[];  // hmax * 3
+    __shared__ FusedShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const long long wg = (long long)warp * gridDim.x + blockIdx.x;
+    const long long nwg = (long long)gridDim.x * nwarps;
+    const long long vstride = a.Nf_pad * 4;
+    const long long n_groups = (a.n_slices + FS_SLICES - 1) / FS_SLICES;
+    unsigned epoch = 0;
+
+    if (threadIdx.x < a.n_sys) {
+        sh.done[threadIdx.x] = a.state[threadIdx.x].active ? 0 : 1;
+        sh.iters[threadIdx.x] = 0;
+        sh.alpha[threadIdx.x] = 0.0;
+        sh.beta[threadIdx.x] = 0.0;
+        sh.lastcur[threadIdx.x] = 1;
+    }
+    for (int i = threadIdx.x; i < 3 * F_MAX_SYS * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
+    __syncthreads();
+
+    // generation "-1": r_0 = b, p = 0, Ap = 0; x = 0
+    for (int s = 0; s < a.n_sys; s++) {
+        double acc = 0.0;
+        if (!sh.done[s]) {
+            const double4 *b4 = (const double4 *)(a.b + s * vstride);
+            double4 *x4 = (double4 *)(a.x + s * vstride), *R1 = (double4 *)(a.r1 + s * vstride), *P1 = (double4 *)(a.p1 + s * vstride),
+                    *A1 = (double4 *)(a.Ap1 + s * vstride);
+            for (long long sl = wg; sl < a.n_slices; sl += nwg) {
+                const long long row = sl * 32 + lane;
+                const double4 bv = b4[row];
+                x4[row] = make_double4(0.0, 0.0, 0.0, 0.0);
+                P1[row] = make_double4(0.0, 0.0, 0.0, 0.0);
+                A1[row] = make_double4(0.0, 0.0, 0.0, 0.0);
+                R1[row] = bv;
+                acc += bv.x * bv.x + bv.y * bv.y + bv.z * bv.z;
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sh.warp[0][s][warp] = acc;
+    }
+    fused_allreduce<1, 10>(a, grid, sh, epoch, [&](int ss, double t0, double, double) {
+        sh.normb[ss] = t0;
+        sh.rho[ss] = t0;
+        sh.tot0[ss] = t0;
+        if (!sh.done[ss] && t0 == 0.0) sh.done[ss] = 1;
+    });
+
+    int cur = 0;
+    for (long long it = 1; it <= a.maxiter; it++) {
+        int all = 1;
+        for (int q = 0; q < a.n_sys; q++) all &= sh.done[q];
+        if (all) break;
+        for (int s = 0; s < a.n_sys; s++) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            if (!sh.done[s]) {
+                const double alpha = sh.alpha[s], beta = sh.beta[s];
+                const double4 *Ro = (const double4 *)((cur ? a.r : a.r1) + s * vstride);
+                const double4 *Po = (const double4 *)((cur ? a.p0 : a.p1) + s * vstride);
+                const double4 *Ao = (const double4 *)((cur ? a.Ap : a.Ap1) + s * vstride);
+                double4 *Rn = (double4 *)((cur ? a.r1 : a.r) + s * vstride);
+                double4 *Pn = (double4 *)((cur ? a.p1 : a.p0) + s * vstride);
+                double4 *An = (double4 *)((cur ? a.Ap1 : a.Ap) + s * vstride);
+                double4 *X4 = (double4 *)(a.x + s * vstride);
+                const double *vals = a.val + (long long)s * a.n_slots * 9;
+                for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+                    const int h0 = a.halo_ptr[g], nh = a.halo_ptr[g + 1] - h0;
+                    for (int hb = threadIdx.x; hb < nh; hb += 3 * FS_THREADS) {
+                        int node[3];
+                        double4 rv[3], pv[3], av[3];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const int h = hb + k * FS_THREADS;
+                            node[k] = a.halo_nodes[h0 + (h < nh ? h : hb)];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            rv[k] = ld_node(Ro + node[k]);
+                            av[k] = ld_node(Ao + node[k]);
+                            pv[k] = ld_node(Po + node[k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const int h = hb + k * FS_THREADS;
+                            if (h < nh) {
+                                hv[3 * h] = fma(beta, pv[k].x, fma(-alpha, av[k].x, rv[k].x));
+                                hv[3 * h + 1] = fma(beta, pv[k].y, fma(-alpha, av[k].y, rv[k].y));
+                                hv[3 * h + 2] = fma(beta, pv[k].z, fma(-alpha, av[k].z, rv[k].z));
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const long long sl = g * FS_SLICES + warp;
+                    if (sl < a.n_slices) {
+                        const long long row = sl * 32 + lane;
+                        const int q0 = a.slice_ptr[sl];
+                        const int w = (a.slice_ptr[sl + 1] - q0) >> 5;
+                        const double *v = vals + (long long)(q0 >> 5) * 288 + lane;
+                        const unsigned short *lc = a.lcol + q0 + lane;
+                        const double4 ro = Ro[row], ao = Ao[row], po = Po[row];
+                        double4 xv = X4[row];
+                        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                        for (int j0 = 0; j0 < w; j0 += STR_BATCH) {
+                            int c[STR_BATCH];
+                            double m[STR_BATCH][9];
+#pragma unroll
+                            for (int k = 0; k < STR_BATCH; k++) {
+                                const int jj = (j0 + k < w) ? j0 + k : j0;
+                                c[k] = lc[32 * jj];
+#pragma unroll
+                                for (int q = 0; q < 9; q++) m[k][q] = v[288 * jj + 32 * q];
+                            }
+#pragma unroll
+                            for (int k = 0; k < STR_BATCH; k++) {
+                                if (j0 + k < w) {
+                                    const double *pj = hv + 3 * c[k];
+                                    const double px = pj[0], py = pj[1], pz = pj[2];
+                                    JF_BLOCK_FMA(m[k], 1, px, py, pz)
+                                }
+                            }
+                        }
+                        // the deferred updates of the previous iteration, then this iteration's publication
+                        xv.x = fma(alpha, po.x, xv.x);
+                        xv.y = fma(alpha, po.y, xv.y);
+                        xv.z = fma(alpha, po.z, xv.z);
+                        const double r0 = fma(-alpha, ao.x, ro.x), r1 = fma(-alpha, ao.y, ro.y), r2 = fma(-alpha, ao.z, ro.z);
+                        const double p0 = fma(beta, po.x, r0), p1 = fma(beta, po.y, r1), p2 = fma(beta, po.z, r2);
+                        X4[row] = xv;
+                        Rn[row] = make_double4(r0, r1, r2, 0.0);
+                        Pn[row] = make_double4(p0, p1, p2, 0.0);
+                        An[row] = make_double4(y0, y1, y2, 0.0);
+                        a0 += p0 * y0 + p1 * y1 + p2 * y2;
+                        a1 += r0 * y0 + r1 * y1 + r2 * y2;
+                        a2 += y0 * y0 + y1 * y1 + y2 * y2;
+                    }
+                    __syncthreads();
+                }
+            }
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+            a2 = warp_sum(a2);
+            if (lane == 0) {
+                sh.warp[0][s][warp] = a0;
+                sh.warp[1][s][warp] = a1;
+                sh.warp[2][s][warp] = a2;
+            }
+        }
+        fused_allreduce<3, 10>(a, grid, sh, epoch, [&](int ss, double pAp, double rAp, double ApAp) {
+            if (sh.done[ss]) return;
+            const double rho = sh.rho[ss];
+            const double alpha = rho / pAp;
+            const double rsnew = fma(alpha * alpha, ApAp, fma(-2.0 * alpha, rAp, rho));
+            sh.alpha[ss] = alpha;
+            sh.iters[ss] = (int)it;
+            sh.lastcur[ss] = cur;  // generation that holds this iteration's p
+            if (rsnew < a.tol * sh.normb[ss] || it == a.maxiter || !(rsnew > 0.0)) {
+                sh.done[ss] = 1;
+            } else {
+                sh.beta[ss] = rsnew / rho;
+                sh.rho[ss] = rsnew;
+            }
+        });
+        cur ^= 1;
+    }
+
+    // the last iteration's x += alpha p, then (A12) U[free] += step * x ; du = step^2 * sum x^2
+    for (int s = 0; s < a.n_sys; s++) {
+        double acc = 0.0;
+        if (a.state[s].active) {
+            const double alpha = sh.alpha[s];
+            const double4 *P4 = (const double4 *)((sh.lastcur[s] ? a.p1 : a.p0) + s * vstride);
+            double4 *X4 = (double4 *)(a.x + s * vstride);
+            double *U = a.U + (long long)s * a.N * 3;
+            for (long long sl = wg; sl < a.n_slices; sl += nwg) {
+                const long long row = sl * 32 + lane;
+                const double4 pv = P4[row];
+                double4 xv = X4[row];
+                xv.x = fma(alpha, pv.x, xv.x);
+                xv.y = fma(alpha, pv.y, xv.y);
+                xv.z = fma(alpha, pv.z, xv.z);
+                X4[row] = xv;
+                if (a.apply_update && row < a.Nf) {
+                    U[3 * row] += a.step * xv.x;
+                    U[3 * row + 1] += a.step * xv.y;
+                    U[3 * row + 2] += a.step * xv.z;
+                    acc += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z;
+                }
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sh.warp[0][s][warp] = acc;
+    }
+    if (a.apply_update) fused_allreduce<1, 10>(a, grid, sh, epoch, [&](int ss, double t0, double, double) { sh.tot0[ss] = t0; });
     if (blockIdx.x == 0 && threadIdx.x < a.n_sys && a.state[threadIdx.x].active) {
         const int q = threadIdx.x;
         a.state[q].cg_iters = sh.iters[q];
@@ -316,6 +535,37 @@ int jf_cg_fused_configure(jf_ctx *c) {
     c->cg_fused_smem = smem;
     c->cg_fused = 1;
     return 1;
+}
+
+// streaming counterpart: needs the group halo lists of the halo-staged streaming kernel (cg_stream_halo)
+int jf_cg_fused_stream_configure(jf_ctx *c) {
+    c->cg_fused_stream = 0;
+    if (!c->cg_stream_halo || c->n_sys > F_MAX_SYS || getenv("JF_CG_CLASSIC")) return 0;
+    const size_t smem = (size_t)c->cg_hmax * 3 * sizeof(double);
+    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_stream_kernel, FS_THREADS, smem));
+    if (per_sm < 1) return 0;
+    const long long n_groups = (c->n_slices + FS_SLICES - 1) / FS_SLICES;
+    long long grid = std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(n_groups, c->sm_count));
+    if (grid > 320) grid = 320;  // the collect keeps ten partial sums per lane
+    c->cg_fused_stream_grid = (int)grid;
+    c->cg_fused_smem = smem;
+    c->cg_fused_stream = 1;
+    return 1;
+}
+
+int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
+    a.halo_ptr = c->d_halo_ptr;
+    a.halo_nodes = c->d_halo_nodes;
+    a.lcol = c->d_lcol;
+    a.hmax = c->cg_hmax;
+    a.r1 = c->d_r1;
+    a.Ap1 = c->d_Ap1;
+    void *args[] = {&a};
+    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_fused_stream_kernel, dim3(c->cg_fused_stream_grid), dim3(FS_THREADS), args,
+                                        c->cg_fused_smem, c->stream));
+    return 0;
 }
 
 int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {

@@ -229,7 +229,8 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
     from jointforces_b200 import _lib
     c = make_case(0.3, 100.0)
     res = []
-    for flags, no_regres, classic in ((0, False, False), (0, False, True), (0, True, True), (_lib.JF_FLAG_NO_RESIDENT, False, True)):
+    NR = _lib.JF_FLAG_NO_RESIDENT
+    for flags, no_regres, classic in ((0, False, False), (0, False, True), (0, True, True), (NR, False, False), (NR, False, True)):
         for name, on in (("JF_CG_NO_REGRES", no_regres), ("JF_CG_CLASSIC", classic)):
             if on:
                 monkeypatch.setenv(name, "1")
@@ -243,23 +244,28 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
             info = ctx.info()
             res.append((ctx.displacements(), cgit[0], (info["cg_resident"], info["cg_fused"])))
     kinds = [r[2] for r in res]
-    # single-reduction register kernel / classic register kernel / classic shared-memory kernel / classic streaming kernel
-    assert kinds == [(2, 1), (2, 0), (1, 0), (0, 0)], kinds
-    for other in res[:3]:
+    # single-reduction register kernel / classic register kernel / classic shared-memory kernel /
+    # single-reduction streaming kernel / classic streaming kernel
+    assert kinds == [(2, 1), (2, 0), (1, 0), (0, 2), (0, 0)], kinds
+    for other in res[:4]:
         # CG's loose stop makes the iteration count rounding-sensitive (DESIGN.md "Trajectory sensitivity")
-        assert np.abs(other[1].astype(int) - res[3][1]).max() <= 0.05 * res[3][1].max()
-        assert np.linalg.norm(other[0] - res[3][0]) / np.linalg.norm(res[3][0]) < 5e-5
+        assert np.abs(other[1].astype(int) - res[4][1]).max() <= 0.05 * res[4][1].max()
+        assert np.linalg.norm(other[0] - res[4][0]) / np.linalg.norm(res[4][0]) < 5e-5
 
 
-def test_resident_batch_of_two_systems(beams):
-    """Two load cases small enough to be resident together (one CTA group per system)."""
+@pytest.mark.parametrize("streamed", [False, True])
+def test_batch_of_two_systems(beams, streamed):
+    """Two load cases in lockstep: small enough to be resident together (one CTA group per system), and through
+    the streaming kernels (systems finish their CG solves at different iterations)."""
     from jointforces_b200 import _lib
     cases = [make_case(0.667, p) for p in (10.0, 1000.0)]
     singles = [_lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
                                             COLLAGEN12, 0.0033, 30, 0.01, beams=beams) for c in cases]
     c0 = cases[0]
-    with _lib.Context(c0["coords"], c0["tets"], c0["movable"], n_sys=2, beams=beams) as ctx:
-        assert ctx.info()["cg_resident"] in (1, 2)
+    with _lib.Context(c0["coords"], c0["tets"], c0["movable"], n_sys=2, beams=beams,
+                      flags=_lib.JF_FLAG_NO_RESIDENT if streamed else 0) as ctx:
+        info = ctx.info()
+        assert (info["cg_resident"], info["cg_fused"]) == ((0, 2) if streamed else (2, 1)), info
         ctx.set_material(*COLLAGEN12)
         for s, c in enumerate(cases):
             ctx.set_targets(c["f_target"], s)
@@ -268,7 +274,7 @@ def test_resident_batch_of_two_systems(beams):
         for s in range(2):
             # the grid (hence the summation order of the dot products) differs from the single-system
             # launch, so agreement is to rounding-amplified-by-CG level, not bitwise
-            assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= 2
+            assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= max(2, 0.02 * singles[s]["cg_iters"].max())
             assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < 2e-5
 
 
