@@ -35,7 +35,9 @@ enum jf_status {
     JF_ERR_ARG = -1,    /* bad argument (null pointer, size, index out of range, degenerate tet) */
     JF_ERR_CUDA = -2,   /* CUDA runtime error or no device */
     JF_ERR_STATE = -3,  /* call out of order (e.g. relax before material/targets are set) */
-    JF_ERR_NOMEM = -4
+    JF_ERR_NOMEM = -4,
+    JF_ERR_IO = -5,     /* file cannot be opened or read */
+    JF_ERR_FORMAT = -6  /* input is outside what the fast path handles; the caller falls back to the reference's own loop */
 };
 
 /* jf_ctx_create flags */
@@ -141,7 +143,7 @@ typedef struct jf_info {
     int64_t bytes_device;
     int32_t cg_resident /* 2: matrix in registers, 1: in shared memory, for the whole CG solve; 0: streamed */, cg_wmax;
     int32_t cg_stream_halo /* streaming kernel with per-group halo staging */;
-    int32_t cg_fused /* register-resident kernel with one grid barrier per CG iteration */;
+    int32_t cg_fused /* one grid barrier per CG iteration: 1 register-resident kernel, 2 streaming kernel */;
 } jf_info;
 int jf_get_info(jf_ctx *ctx, jf_info *out);
 
@@ -158,6 +160,23 @@ int jf_solve_boundarycondition(int device, int64_t n_nodes, const double *nodes,
 
 /* FP64 FMA micro-benchmark (roofline denominator for the element kernel): returns GFLOP/s */
 int jf_bench_fp64(int device, double *gflops);
+
+/*
+ * Mesh ingestion: read_meshfile (jointforces/simulation.py:25-78) without the Python line loop.  Host code only.
+ * jf_msh_open reads the file, finds the first "$Nodes" / "$Elements" lines and the optional "$Jointforces" block
+ * (has_radii = 1: r_inner, r_outer in the file's unit, micrometres; the caller scales by 10**-6 as :52-53 does);
+ * jf_msh_read converts the node lines (tokens after the first -> coords (n_nodes,3)) and the element lines (LAST
+ * four tokens, minus one -> tets (n_elements,4), as doubles like the reference returns them and/or as int32 like
+ * jf_ctx_create takes them; either pointer may be NULL) on n_threads host threads (<= 0: all cores).  Numbers are
+ * converted correctly rounded, i.e. bit-identical to Python's float().  Files the line loop would treat
+ * differently from a plain decimal ASCII file return JF_ERR_FORMAT: the caller then runs the reference's loop,
+ * which raises what the reference raises.
+ */
+typedef struct jf_msh jf_msh;
+int jf_msh_open(const char *path, jf_msh **out, int64_t *n_nodes, int64_t *n_elements, int32_t *has_radii, double *r_inner,
+                double *r_outer);
+int jf_msh_read(jf_msh *msh, double *coords, double *tets_f64, int32_t *tets_i32, int32_t n_threads);
+void jf_msh_close(jf_msh *msh);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,7 @@ SYMBOLS = [
     "jf_set_targets", "jf_set_displacements", "jf_get_displacements", "jf_restore_displacements", "jf_get_forces", "jf_evaluate", "jf_get_energy",
     "jf_get_element_quantities", "jf_get_stiffness_blocks", "jf_cg", "jf_get_cg_solution", "jf_relax", "jf_get_stats",
     "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64", "jf_set_curve_bins", "jf_get_curves", "jf_apply_stiffness",
+    "jf_msh_open", "jf_msh_read", "jf_msh_close",
 ]
 
 
@@ -98,9 +99,14 @@ def load():
     L.jf_apply_stiffness.argtypes = [_vp, C.c_int, _dp, _dp]
     L.jf_set_curve_bins.argtypes = [_vp, C.c_int, _ip, _vp, C.c_double]
     L.jf_get_curves.argtypes = [_vp, _dp]
+    L.jf_msh_open.argtypes = [C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                              C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.jf_msh_read.argtypes = [_vp, _vp, _vp, _vp, C.c_int32]
+    L.jf_msh_close.argtypes = [_vp]
+    L.jf_msh_close.restype = None
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("jf_last_error", "jf_ctx_destroy"):
+        if name not in ("jf_last_error", "jf_ctx_destroy", "jf_msh_close"):
             fn.restype = C.c_int
     _lib = L
     return L
@@ -118,6 +124,33 @@ def device_count():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
+
+
+JF_ERR_FORMAT = -6
+
+
+def read_msh(path, want_int32=False, n_threads=0):
+    """Threaded Gmsh 2.2 ASCII reader (jf_msh_*).  Returns ``(coords (N,3) in file units, tets (T,4) 0-based as
+    float64 -- or int32 with ``want_int32`` --, radii)`` with ``radii = (r_inner, r_outer)`` in micrometres or None
+    when the file has no ``$Jointforces`` block; returns None for files the fast path leaves to the line loop."""
+    L = load()
+    h = _vp()
+    nn, ne, has = C.c_int64(), C.c_int64(), C.c_int32()
+    ri, ro = C.c_double(), C.c_double()
+    rc = L.jf_msh_open(os.fsencode(path), C.byref(h), C.byref(nn), C.byref(ne), C.byref(has), C.byref(ri), C.byref(ro))
+    if rc == JF_ERR_FORMAT:
+        return None
+    check(rc)
+    try:
+        coords = np.empty((nn.value, 3), dtype=np.float64)
+        tets = np.empty((ne.value, 4), dtype=np.int32 if want_int32 else np.float64)
+        rc = L.jf_msh_read(h, _ptr(coords), None if want_int32 else _ptr(tets), _ptr(tets) if want_int32 else None, n_threads)
+        if rc == JF_ERR_FORMAT:
+            return None
+        check(rc)
+    finally:
+        L.jf_msh_close(h)
+    return coords, tets, ((ri.value, ro.value) if has.value else None)
 
 
 class Context:

@@ -19,27 +19,30 @@ from glob import glob
 
 import numpy as np
 
+from . import _lib
 from .solver import Solver, SemiAffineFiberMaterial, load_solver  # noqa: F401  (re-exported like the reference)
 
 
 # --------------------------------------------------------------------------------------------------
 # mesh file (reference simulation.py:25-78)
 # --------------------------------------------------------------------------------------------------
-def _parse_block(lines, start, count, take_last):
-    """Rows ``start .. start+count`` of ``lines`` as a float array of their last ``take_last``
-    tokens.  Vectorised when every row has the same token count, else the reference's line loop."""
+def _parse_block(lines, start, count, width, after_first=False):
+    """Rows ``start .. start+count`` of ``lines`` as a ``(count, width)`` float array of their last ``width`` tokens
+    (elements, reference :70) or of all tokens after the first (nodes, reference :60 -- then there must be exactly
+    ``width`` of them).  Vectorised when every row has the same token count, else the reference's line loop."""
     if count == 0:
-        return np.zeros((0, take_last))
+        return np.zeros((0, width))
     first = lines[start].split()
     try:
         flat = np.array(" ".join(lines[start:start + count]).split(), dtype=np.float64)
-        if flat.size != count * len(first):
+        if flat.size != count * len(first) or (after_first and len(first) != width + 1) or len(first) < width:
             raise ValueError
-        return flat.reshape(count, len(first))[:, -take_last:]
+        return flat.reshape(count, len(first))[:, -width:]
     except ValueError:
-        out = np.zeros((count, take_last))
+        out = np.zeros((count, width))
         for i in range(count):
-            out[i] = lines[start + i].split()[-take_last:]
+            tokens = lines[start + i].split()
+            out[i] = np.array([float(x) for x in tokens[1:]]) if after_first else tokens[-width:]
         return out
 
 
@@ -47,6 +50,36 @@ def read_meshfile(meshfile, r_inner=None, r_outer=None):
     """Parse a Gmsh 2.2 ASCII mesh.  Returns ``coords (N,3) [m], tets (T,4) float 0-based,
     r_inner [m], r_outer [m]`` exactly like the reference: radii found in a ``$Jointforces``
     block override the arguments, every ``$Elements`` line contributes its last four tokens."""
+    fast = _read_meshfile_fast(meshfile, r_inner, r_outer)
+    if fast is not None:
+        return fast
+    return _read_meshfile_lines(meshfile, r_inner, r_outer)
+
+
+def _read_meshfile_fast(meshfile, r_inner, r_outer):
+    """The regular case through the library's threaded reader (jf_msh_*, bit-identical numbers); None when the
+    library leaves the file to the line loop (anything but plain decimal ASCII) or has not been built."""
+    try:
+        res = _lib.read_msh(meshfile)
+    except _lib.JFError:
+        res = None
+    if res is None:
+        return None
+    coords, tets, radii = res
+    if radii is not None:
+        r_inner, r_outer = radii
+        print('Geometry for spherical contraction is defined in mesh file (r_inner={:.2f}, r_outer={:.2f}).'.format(r_inner, r_outer))
+        print('Will ignore user-defined values of r_inner and r_outer.')
+    else:
+        if r_inner is None:
+            raise ValueError('r_inner not defined')
+        if r_outer is None:
+            raise ValueError('r_outer not defined')
+    return coords, tets, r_inner * 10 ** -6, r_outer * 10 ** -6
+
+
+def _read_meshfile_lines(meshfile, r_inner=None, r_outer=None):
+    """The reference's line loop (simulation.py:25-78), vectorised per block where the rows are regular."""
     with open(meshfile, 'r') as f:
         lines = f.readlines()
 
@@ -76,7 +109,7 @@ def read_meshfile(meshfile, r_inner=None, r_outer=None):
 
     i_nodes = lines.index('$Nodes\n')
     n_nodes = int(lines[i_nodes + 1])
-    coords = np.ascontiguousarray(_parse_block(lines, i_nodes + 2, n_nodes, 3))
+    coords = np.ascontiguousarray(_parse_block(lines, i_nodes + 2, n_nodes, 3, after_first=True))
 
     i_elem = lines.index('$Elements\n')
     n_elem = int(lines[i_elem + 1])

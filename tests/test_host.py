@@ -55,6 +55,67 @@ def test_meshfile_roundtrip(tmp_path):
     assert len(np.unique(t)) == len(coords)                                          # no orphan nodes
 
 
+@pytest.mark.parametrize("name", ["gmsh_like", "with_block", "ragged", "generated"])
+def test_meshfile_matches_reference_function(tmp_path, name):
+    """The reference's own read_meshfile (simulation.py:25-78), run by tests/golden/make_reference_functions.py:
+    both readers (the library's threaded one and the line loop it falls back to) return its arrays bit for bit."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_meshfile.npz"))
+    path = tmp_path / (name + ".msh")
+    path.write_text(str(g[name + "_text"]))
+    fast = sim._read_meshfile_fast(str(path), 7.0, 9.0)
+    assert fast is not None, "the threaded reader must take plain decimal files"
+    for c, t, ri, ro in (fast, sim._read_meshfile_lines(str(path), 7.0, 9.0), sim.read_meshfile(str(path), 7.0, 9.0)):
+        assert c.dtype == np.float64 and t.dtype == np.float64
+        assert np.array_equal(c.view(np.uint64), g[name + "_coords"].view(np.uint64))     # same bits, signed zeros included
+        assert np.array_equal(t, g[name + "_tets"])
+        assert (ri, ro) == tuple(g[name + "_radii"])
+
+
+def test_meshfile_fast_reader_leaves_irregular_files_to_the_line_loop(tmp_path):
+    """Whatever is not a plain decimal ASCII file takes the reference's loop, with the reference's outcome."""
+    base = "$Nodes\n4\n1 0 0 0\n2 1 0 0\n3 0 1 0\n4 0 0 1\n$EndNodes\n$Elements\n1\n1 4 0 1 2 3 4\n$EndElements\n"
+    variants = {
+        "crlf": base.replace("\n", "\r\n"),                       # universal newlines: the reference parses it
+        "float_ids": base.replace("1 4 0 1 2 3 4", "1 4 0 1.0 2.0 3.0 4.0"),
+        "underscore": base.replace("2 1 0 0", "2 1_0 0 0"),         # float('1_0') == 10.0 in Python
+        "nan_coord": base.replace("2 1 0 0", "2 nan 0 0"),
+        "unicode": base + "$Comment\n\u00b5m\n$EndComment\n",
+    }
+    for name, text in variants.items():
+        path = tmp_path / (name + ".msh")
+        path.write_text(text, newline="") if name == "crlf" else path.write_text(text, encoding="utf-8")
+        assert sim._read_meshfile_fast(str(path), 1, 2) is None, name
+        c, t, ri, ro = sim.read_meshfile(str(path), 1, 2)
+        assert c.shape == (4, 3) and np.array_equal(t, [[0, 1, 2, 3]]), name
+    assert sim.read_meshfile(str(tmp_path / "underscore.msh"), 1, 2)[0][1, 0] == 10.0
+    # errors are the line loop's errors
+    for name, text, exc in (("short_node", base.replace("2 1 0 0", "2 1 0"), ValueError),
+                            ("no_nodes", base.replace("$Nodes", "$Knots"), ValueError),
+                            ("too_few", base.replace("$Elements\n1", "$Elements\n5"), ValueError),
+                            ("truncated", base.replace("$Elements\n1", "$Elements\n5").replace("$EndElements\n", ""), IndexError),
+                            ("block_without_radii", base + "$Jointforces\ninfo=x\n$EndJointforces\n", KeyError)):
+        path = tmp_path / (name + ".msh")
+        path.write_text(text)
+        assert sim._read_meshfile_fast(str(path), 1, 2) is None, name
+        with pytest.raises(exc):
+            sim.read_meshfile(str(path), 1, 2)
+    with pytest.raises(FileNotFoundError):
+        sim.read_meshfile(str(tmp_path / "missing.msh"), 1, 2)
+
+
+def test_meshfile_fast_reader_large_file_equals_line_loop(tmp_path):
+    """60 k tets with full-precision coordinates: identical arrays, int32 connectivity on request."""
+    from jointforces_b200 import _lib
+    coords, tets = jf.mesh.spherical_inclusion(str(tmp_path / "m.msh"), 100, 10000, 0.06)
+    a = sim._read_meshfile_fast(str(tmp_path / "m.msh"), None, None)
+    b = sim._read_meshfile_lines(str(tmp_path / "m.msh"))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2:] == b[2:]
+    assert np.array_equal(a[0], coords) and len(a[1]) == len(tets) > 50000
+    for threads in (1, 3):
+        c32, t32, radii = _lib.read_msh(str(tmp_path / "m.msh"), want_int32=True, n_threads=threads)
+        assert t32.dtype == np.int32 and np.array_equal(t32, tets) and np.array_equal(c32, coords) and radii == (100.0, 10000.0)
+
+
 def test_meshfile_without_trailer_and_ragged_elements(tmp_path):
     path = tmp_path / "r.msh"
     path.write_text("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n4\n1 0 0 0\n2 1 0 0\n3 0 1 0\n4 0 0 1\n$EndNodes\n"
