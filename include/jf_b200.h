@@ -178,6 +178,38 @@ int jf_msh_open(const char *path, jf_msh **out, int64_t *n_nodes, int64_t *n_ele
 int jf_msh_read(jf_msh *msh, double *coords, double *tets_f64, int32_t *tets_i32, int32_t n_threads);
 void jf_msh_close(jf_msh *msh);
 
+/*
+ * Lookup-table interpolants and pressure inference on the device (the consumer side of the table).
+ *
+ * jf_table_create: one scipy LinearNDInterpolator (jointforces/simulation.py:608 and :613) -- piecewise-linear
+ * interpolation of `values` (n_points) over the Delaunay triangulation of `points` (n_points,2), NaN outside the
+ * hull.  The caller passes the triangulation scipy.spatial.Delaunay(points) gives (what LinearNDInterpolator builds
+ * internally): simplices (n_simplices,3) int32, transform (n_simplices,3,2), neighbors (n_simplices,3) int32.
+ * jf_table_eval: out[i] = f(x_i, y_i) with optional log of either coordinate and exp of the result:
+ *   get_displacement(distance, pressure) = f(log distance, log pressure)         (:610-611)  log_x=1 log_y=1 exp_out=0
+ *   get_pressure(distance, displacement) = exp(f_inv(log distance, displacement)) (:615-616)  log_x=1 log_y=0 exp_out=1
+ * jf_infer_pressure: force.py:399-432 for one frame of PIV vectors, NaN-coded like the reference; outputs are the
+ * kept vectors in input order.  cos_min = cos(2 pi angle_filter / 360); use_filter = 0 for angle_filter=None.
+ * jf_reconstruct_frames: the per-frame loop of reconstruct, force.py:70-121, for all frames of a series in one
+ * call: stats (n_frames,76) = nanmean, nanmedian, nanstd(ddof=1), number of pressures used, 72 sector nanmeans.
+ * r_min / r_max: NaN stands for None.  sector_bounds (72,2) = (alpha-5)*pi/180, (alpha+5)*pi/180 for
+ * alpha = -180, -175 .. 175, as the caller computes them.
+ * Agreement with scipy/numpy: to rounding (libm and CUDA log/exp/atan2 differ in the last bit; a query on a shared
+ * edge may be assigned to the other triangle); medians are exact order statistics.
+ */
+typedef struct jf_table jf_table;
+int jf_table_create(jf_table **out, int device, int64_t n_points, const double *points, const double *values, int64_t n_simplices,
+                    const int32_t *simplices, const double *transform, const int32_t *neighbors);
+void jf_table_destroy(jf_table *table);
+int jf_table_eval(jf_table *table, int64_t n, const double *xq, const double *yq, int log_x, int log_y, int exp_out, double *out);
+int jf_infer_pressure(jf_table *table, int64_t n, const double *x, const double *y, const double *u, const double *v, double cx,
+                      double cy, double r_sph, int use_filter, double cos_min, double *distance, double *displacement,
+                      double *angle, double *pressure, int64_t *n_out);
+int jf_reconstruct_frames(jf_table *table, int32_t n_frames, const int64_t *frame_ptr, const double *frames /* (n_frames,3): cx, cy, r */,
+                          const double *x, const double *y, const double *u, const double *v, int use_filter, double cos_min,
+                          double r_min, double r_max, const double *sector_bounds, double *stats);
+int64_t jf_table_launches(jf_table *table); /* kernels launched so far (measurement) */
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ SYMBOLS = [
     "jf_get_element_quantities", "jf_get_stiffness_blocks", "jf_cg", "jf_get_cg_solution", "jf_relax", "jf_get_stats",
     "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64", "jf_set_curve_bins", "jf_get_curves", "jf_apply_stiffness",
     "jf_msh_open", "jf_msh_read", "jf_msh_close",
+    "jf_table_create", "jf_table_destroy", "jf_table_eval", "jf_infer_pressure", "jf_reconstruct_frames", "jf_table_launches",
 ]
 
 
@@ -104,9 +105,20 @@ def load():
     L.jf_msh_read.argtypes = [_vp, _vp, _vp, _vp, C.c_int32]
     L.jf_msh_close.argtypes = [_vp]
     L.jf_msh_close.restype = None
+    _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+    L.jf_table_create.argtypes = [C.POINTER(_vp), C.c_int, C.c_int64, _dp, _dp, C.c_int64, _ip, _dp, _ip]
+    L.jf_table_destroy.argtypes = [_vp]
+    L.jf_table_destroy.restype = None
+    L.jf_table_eval.argtypes = [_vp, C.c_int64, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]
+    L.jf_infer_pressure.argtypes = [_vp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                                    _dp, _dp, _dp, _dp, C.POINTER(C.c_int64)]
+    L.jf_reconstruct_frames.argtypes = [_vp, C.c_int32, _lp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        _dp, _dp]
+    L.jf_table_launches.argtypes = [_vp]
+    L.jf_table_launches.restype = C.c_int64
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("jf_last_error", "jf_ctx_destroy", "jf_msh_close"):
+        if name not in ("jf_last_error", "jf_ctx_destroy", "jf_msh_close", "jf_table_destroy", "jf_table_launches"):
             fn.restype = C.c_int
     _lib = L
     return L

@@ -274,8 +274,10 @@ def test_batch_of_two_systems(beams, streamed):
         for s in range(2):
             # the grid (hence the summation order of the dot products) differs from the single-system
             # launch, so agreement is to rounding-amplified-by-CG level, not bitwise
-            assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= max(2, 0.02 * singles[s]["cg_iters"].max())
-            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < 2e-5
+            # (the streamed run also differs from the singles in kernel: CG's loose stop makes the iteration count
+            # rounding-sensitive, DESIGN.md "Trajectory sensitivity")
+            assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= (0.15 * singles[s]["cg_iters"].max() if streamed else 2)
+            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < (5e-5 if streamed else 2e-5)
 
 
 # ---- edge cases and error behaviour -----------------------------------------------------------------------

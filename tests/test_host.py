@@ -334,6 +334,30 @@ def test_no_cpu_fallback_without_device():
     M.set_nodes(nodes); M.set_tetrahedra(np.array([[0, 1, 2, 3]]))
     with pytest.raises(_lib.JFError):
         M.solve_boundarycondition()
+    # the table interpolants and everything behind them live on the device as well
+    table = {'pressure': np.array([1.0, 10.0, 100.0]), 'x': np.array([1.0, 2.0, 4.0]),
+             'y': np.array([[1e-3, 5e-4, 2e-4], [1e-2, 5e-3, 2e-3], [1e-1, 5e-2, 2e-2]])}
+    with pytest.raises(_lib.JFError, match="CUDA"):
+        jf.force.create_lookup_functions(table)
+
+
+def test_force_host_side_logic():
+    """File ordering, argument checks and the callable protocol of the force module (no device needed)."""
+    from jointforces_b200 import force
+    names = ["def10.npy", "def2.npy", "def000001.npy", "defA3.npy"]
+    assert sorted(names, key=force._natural_key) == ["def000001.npy", "def2.npy", "def10.npy", "defA3.npy"]
+    assert force._filter_args(None) == (0, 0.0)
+    assert force._filter_args(20) == (1, float(np.cos(2 * np.pi * 20 / 360)))
+    with pytest.raises(TypeError, match="device"):
+        force.infer_pressure([1.0], [1.0], [1.0], [1.0], 0.0, 0.0, 1.0, lambda a, b: a)
+    with pytest.raises(TypeError):
+        force.reconstruct_frames([], lambda a, b: a)
+    assert len(force.COLUMNS) == 12 and force.SECTOR_ANGLES[0] == -180 and force.SECTOR_ANGLES[-1] == 175 and len(force.SECTOR_ANGLES) == 72
+    import inspect
+    assert list(inspect.signature(force.infer_pressure).parameters) == ['x_rav', 'y_rav', 'u_rav', 'v_rav', 'x_sph', 'y_sph', 'r_sph',
+                                                                        'get_pressure', 'angle_filter']
+    assert list(inspect.signature(force.reconstruct).parameters)[:8] == ['folder', 'lookupfile', 'muperpixel', 'outfile', 'r_min',
+                                                                         'angle_filter', 'r_max', 'continuous_radii']
 
 
 def test_product_never_imports_the_oracle():
