@@ -149,6 +149,143 @@ def make_lookup_golden():
         len(out), np.isnan(pres).sum(), pres.size, out["reconstruct_default"][:, :3]))
 
 
+class RecordingSolver:
+    """Stands in for saenopy.Solver: records what jointforces hands over, solves nothing.  `save` stores the nodes
+    and a displacement field chosen by the generator so that the reference's curve extraction has data to read."""
+    instances = []
+    field = None            # callable(nodes, pressure) -> (N,3) displacements written by save()
+
+    def __init__(self):
+        self.calls = {}
+        RecordingSolver.instances.append(self)
+
+    def set_material_model(self, m):
+        self.calls["material"] = m
+
+    def set_nodes(self, c):
+        self.calls["nodes"] = np.array(c)
+
+    def set_tetrahedra(self, t):
+        self.calls["tets"] = np.array(t)
+
+    def set_boundary_condition(self, d, f):
+        self.calls["bc_displacement"], self.calls["bc_forces"] = np.array(d), np.array(f)
+
+    def set_initial_displacements(self, u):
+        self.calls["initial"] = np.array(u)
+
+    def solve_boundarycondition(self, **kw):
+        self.calls["solve"] = kw
+
+    def save(self, path):
+        self.calls["save"] = path
+        if RecordingSolver.field is not None:
+            with open(path, "wb") as f:
+                np.savez(f, nodes=self.calls["nodes"], displacements=RecordingSolver.field(self))
+
+
+class _LoadedSolver:
+    def __init__(self, path):
+        class _Mesh:
+            pass
+        z = np.load(path)
+        self.mesh = _Mesh()
+        self.mesh.nodes, self.mesh.displacements = z["nodes"], z["displacements"]
+
+
+def make_simulation_golden():
+    """spherical_contraction_solver (simulation.py:81-168: boundary conditions, parameters.txt, the calls into the
+    solver object), distribute_solver (:171-249: values file, folder names, positional call), extract_deformation_
+    curve_solver and create_lookup_table_solver (:263-323), materials.py -- all the reference's own code, with the
+    saenopy object replaced by a recorder."""
+    import glob as globmod
+    import tempfile
+    from jointforces_b200.mesh import spherical_inclusion
+    out = {}
+    mats = {}
+    exec(compile(open(os.path.join(REF, "materials.py")).read(), os.path.join(REF, "materials.py"), "exec"), mats)
+    for name in ("collagen06", "collagen12", "collagen24", "fibrin40", "matrigel100"):
+        out["material_" + name] = np.array([mats[name][k] for k in ("K_0", "D_0", "L_S", "D_S")], dtype=np.float64)
+    out["material_linear_394"] = np.array([mats["linear"](394)[k] for k in ("K_0", "D_0", "L_S", "D_S")], dtype=np.float64)
+
+    read_meshfile = reference_function("simulation.py", "read_meshfile")
+    g = {"read_meshfile": read_meshfile, "os": os, "Solver": RecordingSolver, "SemiAffineFiberMaterial": lambda *a: tuple(a)}
+    solver_fn = reference_function("simulation.py", "spherical_contraction_solver", g)
+    with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()):
+        # (1) one solve on a small mesh, every argument non-default
+        spherical_inclusion(os.path.join(tmp, "small.msh"), 100, 10000, 0.667)
+        out["small_msh"] = np.array(open(os.path.join(tmp, "small.msh")).read())
+        n_small = len(read_meshfile(os.path.join(tmp, "small.msh"))[0])
+        U0 = np.random.default_rng(1).normal(0, 1e-7, (n_small, 3))
+        RecordingSolver.instances.clear()
+        solver_fn(os.path.join(tmp, "small.msh"), os.path.join(tmp, "one"), 123.456, mats["collagen12"], None, None, False, U0, 55, 0.01, 0.02) \
+            if False else solver_fn(os.path.join(tmp, "small.msh"), os.path.join(tmp, "one"), 123.456, mats["collagen12"], None, None,
+                                    False, U0, 55, 0.01, 0.02)
+        rec = RecordingSolver.instances[-1].calls
+        out["one_material"] = np.array(rec["material"], dtype=np.float64)
+        out["one_nodes"], out["one_tets"] = rec["nodes"], rec["tets"]
+        out["one_bc_displacement"], out["one_bc_forces"], out["one_initial"] = rec["bc_displacement"], rec["bc_forces"], rec["initial"]
+        out["one_solve_kwargs"] = np.array(repr(sorted((k, v if k != "relrecname" else os.path.basename(v)) for k, v in rec["solve"].items())))
+        out["one_save"] = np.array(os.path.basename(rec["save"]))
+        out["one_parameters"] = np.array(open(os.path.join(tmp, "one", "parameters.txt"), encoding="utf-8").read())
+        out["one_U0"] = U0
+
+        # (2) a sweep through distribute_solver with n_cores=1 on a finer mesh; the recorder's save() writes a smooth
+        # radial field scaled with the load so that curve extraction and table building have something to bin
+        spherical_inclusion(os.path.join(tmp, "mid.msh"), 100, 10000, 0.1)
+        g2 = dict(g)
+        g2["spherical_contraction_solver"] = solver_fn
+        g2["load_solver"] = _LoadedSolver
+        g2["sleep"] = lambda s: None
+        dist_fn = reference_function("simulation.py", "distribute_solver", g2)
+
+        def field(solver):
+            nodes = solver.calls["nodes"]
+            r = np.sqrt(np.sum(nodes ** 2., axis=1))
+            load = np.nanmax(np.abs(solver.calls["bc_forces"]))
+            amp = 2e-6 * (load / 1e-10) ** 0.7 * (1e-4 / r) ** 1.8 * (1.0 + 0.3 * np.sin(7.0 * nodes[:, 0] / r))
+            return -nodes / r[:, None] * amp[:, None]
+
+        RecordingSolver.field = field
+        RecordingSolver.instances.clear()
+        seen = []
+        const_args = {"meshfile": os.path.join(tmp, "mid.msh"), "outfolder": os.path.join(tmp, "sweep"), "material": mats["collagen12"],
+                      "max_iter": 77}
+        dist_fn("ignored", const_args, var_arg="pressure", start=0.1, end=10000, n=7, log_scaling=True, n_cores=1,
+                callback=lambda i, n: seen.append((i, n)))
+        out["sweep_const_args_after"] = np.array(repr(sorted(k for k in const_args)))
+        out["sweep_values_txt"] = np.array(open(os.path.join(tmp, "sweep", "pressure-values.txt")).read())
+        out["sweep_listing"] = np.array(sorted(os.listdir(os.path.join(tmp, "sweep"))))
+        out["sweep_callbacks"] = np.array(seen)
+        out["sweep_solve_kwargs"] = np.array(repr(sorted((k, v if k != "relrecname" else os.path.basename(v))
+                                                         for k, v in RecordingSolver.instances[-1].calls["solve"].items())))
+        out["sweep_parameters"] = np.array([open(os.path.join(tmp, "sweep", "simulation%06d" % i, "parameters.txt"), encoding="utf-8").read()
+                                            for i in range(7)])
+        out["sweep_nodes"] = RecordingSolver.instances[-1].calls["nodes"]
+        out["sweep_displacements"] = np.array([np.load(os.path.join(tmp, "sweep", "simulation%06d" % i, "solver.saenopy"))["displacements"]
+                                               for i in range(7)])
+        out["sweep_msh"] = np.array(open(os.path.join(tmp, "mid.msh")).read())
+        # linear branch of the value generator (it spaces the logarithms linearly, :192)
+        const_args = {"meshfile": os.path.join(tmp, "small.msh"), "outfolder": os.path.join(tmp, "lin"), "material": mats["collagen12"]}
+        RecordingSolver.field = None
+        dist_fn("ignored", const_args, start=1, end=100, n=3, log_scaling=False, n_cores=1)
+        out["lin_values_txt"] = np.array(open(os.path.join(tmp, "lin", "pressure-values.txt")).read())
+
+        # (3) the reference's curve extraction and table on those folders
+        g3 = {"load_solver": _LoadedSolver, "glob": globmod.glob, "tqdm": lambda it: it}
+        g3["extract_deformation_curve_solver"] = reference_function("simulation.py", "extract_deformation_curve_solver", g3)
+        table_fn = reference_function("simulation.py", "create_lookup_table_solver", g3)
+        with np.errstate(all="ignore"), __import__("warnings").catch_warnings():
+            __import__("warnings").simplefilter("ignore")
+            table = table_fn(os.path.join(tmp, "sweep"), 1, 50, 100)
+        order = np.argsort(table["pressure"])
+        out["table_pressure"], out["table_x"], out["table_y"] = table["pressure"][order], table["x"], table["y"][order]
+    np.savez_compressed(os.path.join(HERE, "reference_simulation.npz"), **out)
+    print("wrote reference_simulation.npz: %d arrays, sweep mesh %d nodes, populated bins %d of 100\n%s" % (
+        len(out), len(out["sweep_nodes"]), (~np.isnan(out["table_y"][0])).sum(), str(out["one_parameters"])))
+
+
 if __name__ == "__main__":
     make_meshfile_golden()
     make_lookup_golden()
+    make_simulation_golden()

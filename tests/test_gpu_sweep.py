@@ -118,3 +118,51 @@ def test_opt_in_warm_start_chains_load_cases(beams):
     assert all(w < c / 2 for w, c in zip(n_warm[1:], n_cold[1:]))                     # later ones stop after a few steps
     for w, c in zip(warm[1:], cold[1:]):                                              # at nearly the same early-stopped field
         assert np.linalg.norm(w["U"] - c["U"]) < 0.1 * np.linalg.norm(c["U"])
+
+
+# ---- against the reference's own functions (tests/golden/reference_simulation.npz) ---------------------------
+@pytest.fixture(scope="module")
+def ref_sim():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_simulation.npz"))
+
+
+def test_device_curves_equal_reference_table_rows(ref_sim, tmp_path, beams):
+    """The rows the reference's extract_deformation_curve_solver / create_lookup_table_solver computed from the
+    golden displacement fields (simulation.py:263-323), reproduced by the device's radial median: same bits."""
+    from jointforces_b200 import _lib
+    (tmp_path / "mid.msh").write_text(str(ref_sim["sweep_msh"]))
+    coords, tets, r_in, r_out = jf.simulation.read_meshfile(str(tmp_path / "mid.msh"))
+    assert np.array_equal(coords, ref_sim["sweep_nodes"])
+    bc = jf.simulation.spherical_boundary_conditions(coords, r_in, r_out, 1.0)
+    movable = np.any(np.isnan(bc["displacement"]), axis=1)
+    x, _ = jf.simulation.lookup_bins(1, 50, 100)
+    with _lib.Context(coords, tets.astype(np.int32), movable, n_sys=7, beams=beams) as ctx:
+        ctx.set_curve_bins(coords, (r_in * 1e6) * 10 ** -6, x)      # the radius as parameters.txt carries it (:296-297)
+        for s in range(7):
+            ctx.set_displacements(ref_sim["sweep_displacements"][s], s)
+        got = ctx.curves()
+    ref = ref_sim["table_y"]
+    assert got.shape == ref.shape == (7, 100)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got[~np.isnan(ref)].view(np.uint64), ref[~np.isnan(ref)].view(np.uint64))
+
+
+def test_sweep_files_equal_reference_files(ref_sim, tmp_path):
+    """A real sweep on the golden mesh with the generator's arguments: pressure-values.txt and every parameters.txt
+    are the texts the reference's distribute_solver / spherical_contraction_solver wrote."""
+    (tmp_path / "mid.msh").write_text(str(ref_sim["sweep_msh"]))
+    const_args = {"meshfile": str(tmp_path / "mid.msh"), "outfolder": str(tmp_path / "sweep"), "material": jf.materials.collagen12,
+                  "max_iter": 77}
+    jf.simulation.distribute_solver("ignored", const_args, var_arg="pressure", start=0.1, end=10000, n=7, log_scaling=True, n_cores=4)
+    assert open(tmp_path / "sweep" / "pressure-values.txt").read() == str(ref_sim["sweep_values_txt"])
+    assert sorted(os.listdir(tmp_path / "sweep")) == list(ref_sim["sweep_listing"])
+    for i in range(7):
+        folder = tmp_path / "sweep" / ("simulation%06d" % i)
+        assert open(folder / "parameters.txt", encoding="utf-8").read() == str(ref_sim["sweep_parameters"][i])
+        relrec = np.loadtxt(folder / "relrec.txt")
+        assert relrec.ndim == 2 and relrec.shape[1] == 3 and 2 <= len(relrec) <= 78
+    table = jf.simulation.create_lookup_table_solver(str(tmp_path / "sweep"))
+    assert np.array_equal(table["pressure"], ref_sim["table_pressure"]) and np.array_equal(table["x"], ref_sim["table_x"])
+    populated = ~np.isnan(ref_sim["table_y"][0])
+    assert np.array_equal(~np.isnan(table["y"][0]), populated)           # same bins populated
+    assert np.all(np.diff(table["y"][:, populated], axis=0) > 0)
