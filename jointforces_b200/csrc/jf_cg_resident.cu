@@ -404,19 +404,25 @@ int jf_cg_resident_configure(jf_ctx *c) {
     std::vector<int32_t> hptr(ctas + 1, 0), hnodes;
     std::vector<uint16_t> lcol((size_t)c->n_slots, 0);
     int hmax = 1;
-    std::vector<int32_t> tmp;
+    std::vector<std::vector<int32_t>> lists((size_t)ctas);
+    jf_parallel_for(ctas, [&](int64_t lo, int64_t hi) {
+        for (int64_t cb = lo; cb < hi; cb++) {
+            const int64_t s0 = cb * W, s1 = std::min<int64_t>(c->n_slices, s0 + W);
+            const int64_t q0 = c->h_slice_ptr[s0], q1 = c->h_slice_ptr[s1];
+            std::vector<int32_t> &tmp = lists[cb];
+            tmp.assign(c->h_sell_col.begin() + q0, c->h_sell_col.begin() + q1);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            if (tmp.size() > 65535) continue;
+            for (int64_t q = q0; q < q1; q++)
+                lcol[q] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), c->h_sell_col[q]) - tmp.begin());
+        }
+    }, 8);
     for (int cb = 0; cb < ctas; cb++) {
-        const int64_t s0 = (int64_t)cb * W, s1 = std::min<int64_t>(c->n_slices, s0 + W);
-        const int64_t q0 = c->h_slice_ptr[s0], q1 = c->h_slice_ptr[s1];
-        tmp.assign(c->h_sell_col.begin() + q0, c->h_sell_col.begin() + q1);
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        if (tmp.size() > 65535) return 0;
-        for (int64_t q = q0; q < q1; q++)
-            lcol[q] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), c->h_sell_col[q]) - tmp.begin());
-        hnodes.insert(hnodes.end(), tmp.begin(), tmp.end());
+        if (lists[cb].size() > 65535) return 0;
+        hnodes.insert(hnodes.end(), lists[cb].begin(), lists[cb].end());
         hptr[cb + 1] = (int32_t)hnodes.size();
-        hmax = std::max(hmax, (int)tmp.size());
+        hmax = std::max(hmax, (int)lists[cb].size());
     }
     size_t smem = resident_smem(W, c->cg_wmax, hmax);
     int per_sm = 0, variant = 1;

@@ -348,21 +348,27 @@ static int build_group_halos(jf_ctx *c) {
     const int64_t n_groups = (c->n_slices + SH_SLICES - 1) / SH_SLICES;
     std::vector<int32_t> hptr((size_t)n_groups + 1, 0), hnodes;
     std::vector<uint16_t> lcol((size_t)c->n_slots, 0);
-    std::vector<int32_t> tmp;
     int hmax = 1;
+    std::vector<std::vector<int32_t>> lists((size_t)n_groups);
+    jf_parallel_for(n_groups, [&](int64_t lo, int64_t hi) {
+        for (int64_t g = lo; g < hi; g++) {
+            const int64_t s0 = g * SH_SLICES, s1 = std::min<int64_t>(c->n_slices, s0 + SH_SLICES);
+            const int64_t q0 = c->h_slice_ptr[s0], q1 = c->h_slice_ptr[s1];
+            std::vector<int32_t> &tmp = lists[g];
+            tmp.assign(c->h_sell_col.begin() + q0, c->h_sell_col.begin() + q1);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            if (tmp.size() > 65535) continue;
+            for (int64_t q = q0; q < q1; q++)
+                lcol[q] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), c->h_sell_col[q]) - tmp.begin());
+        }
+    }, 8);
     for (int64_t g = 0; g < n_groups; g++) {
-        const int64_t s0 = g * SH_SLICES, s1 = std::min<int64_t>(c->n_slices, s0 + SH_SLICES);
-        const int64_t q0 = c->h_slice_ptr[s0], q1 = c->h_slice_ptr[s1];
-        tmp.assign(c->h_sell_col.begin() + q0, c->h_sell_col.begin() + q1);
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        if (tmp.size() > 65535) return 0;
-        for (int64_t q = q0; q < q1; q++)
-            lcol[q] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), c->h_sell_col[q]) - tmp.begin());
-        hnodes.insert(hnodes.end(), tmp.begin(), tmp.end());
+        if (lists[g].size() > 65535) return 0;
+        hnodes.insert(hnodes.end(), lists[g].begin(), lists[g].end());
         if (hnodes.size() > 2000000000ull) return 0;
         hptr[g + 1] = (int32_t)hnodes.size();
-        hmax = std::max(hmax, (int)tmp.size());
+        hmax = std::max(hmax, (int)lists[g].size());
     }
     int rc;
     if ((rc = jf_dev_alloc(c, &c->d_halo_ptr, hptr.size()))) return rc;

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <thread>
 
 // JF_TIMING=1 in the environment prints the host-side setup stages to stderr
 struct StageTimer {
@@ -33,6 +34,25 @@ struct StageTimer {
         t = n;
     }
 };
+
+// split [0,n) over host threads (structure build only; every use is written so that results do not depend on
+// the thread count)
+template <typename F>
+static inline void jf_parallel_for(int64_t n, F fn, int64_t serial_below = 4096) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 16) nt = 16;
+    if (nt < 2 || n < serial_below) {
+        fn((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t chunk = (n + nt - 1) / nt;
+    for (unsigned i = 0; i < nt; i++) {
+        const int64_t a = i * chunk, b = std::min<int64_t>(n, a + chunk);
+        if (a < b) th.emplace_back([=] { fn(a, b); });
+    }
+    for (auto &t : th) t.join();
+}
 
 void jf_set_error(const char *fmt, ...);
 int jf_cuda_fail(cudaError_t e, const char *what, const char *file, int line);

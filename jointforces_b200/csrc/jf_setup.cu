@@ -13,27 +13,10 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <atomic>
 #include <thread>
 
 #include "jf_internal.h"
-
-// split [0,n) over host threads (structure build only; results do not depend on the thread count)
-template <typename F>
-static void parallel_for(int64_t n, F fn) {
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt > 16) nt = 16;
-    if (nt < 2 || n < 4096) {
-        fn((int64_t)0, n);
-        return;
-    }
-    std::vector<std::thread> th;
-    const int64_t chunk = (n + nt - 1) / nt;
-    for (unsigned i = 0; i < nt; i++) {
-        const int64_t a = i * chunk, b = std::min<int64_t>(n, a + chunk);
-        if (a < b) th.emplace_back([=] { fn(a, b); });
-    }
-    for (auto &t : th) t.join();
-}
 
 // ------------------------------------------------------------------------------------------------
 // direction sphere, saenopy build_beams(300)
@@ -133,28 +116,51 @@ static int build_dirtab(jf_ctx *c, const double *beams, int n_beams) {
 // ------------------------------------------------------------------------------------------------
 // node adjacency (sorted, unique, including self)
 // ------------------------------------------------------------------------------------------------
+// node -> incident (tet, corner) pairs, encoded t*4+m, ascending.  Threads own node ranges and scan all corners
+// for them: no scatter conflicts, same result for any thread count.
+static void build_incidence(int64_t N, int64_t T, const int32_t *tets, std::vector<int32_t> &iptr, std::vector<int32_t> &isrc) {
+    iptr.assign(N + 1, 0);
+    jf_parallel_for(N, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = 0; i < 4 * T; i++) {
+            const int32_t n = tets[i];
+            if (n >= lo && n < hi) iptr[n + 1]++;
+        }
+    });
+    for (int64_t i = 0; i < N; i++) iptr[i + 1] += iptr[i];
+    isrc.resize((size_t)4 * T);
+    jf_parallel_for(N, [&](int64_t lo, int64_t hi) {
+        std::vector<int32_t> fill(iptr.begin() + lo, iptr.begin() + hi);
+        for (int64_t i = 0; i < 4 * T; i++) {
+            const int32_t n = tets[i];
+            if (n >= lo && n < hi) isrc[fill[n - lo]++] = (int32_t)i;
+        }
+    });
+}
+
 static void build_adjacency(int64_t N, int64_t T, const int32_t *tets, std::vector<int64_t> &ptr,
                             std::vector<int32_t> &adj) {
-    std::vector<int64_t> cnt(N + 1, 0);
-    for (int64_t t = 0; t < T; t++)
-        for (int m = 0; m < 4; m++) cnt[tets[4 * t + m] + 1] += 4;
-    for (int64_t i = 0; i < N; i++) cnt[i + 1] += cnt[i];
-    std::vector<int32_t> raw((size_t)cnt[N]);
-    std::vector<int64_t> fill(cnt.begin(), cnt.end() - 1);
-    for (int64_t t = 0; t < T; t++)
-        for (int m = 0; m < 4; m++)
-            for (int r = 0; r < 4; r++) raw[fill[tets[4 * t + m]]++] = tets[4 * t + r];
+    std::vector<int32_t> iptr, isrc;
+    build_incidence(N, T, tets, iptr, isrc);
+    // neighbours of a node (itself included): the corners of its incident tets, sorted, distinct
+    std::vector<int32_t> raw((size_t)4 * iptr[N]);
     ptr.assign(N + 1, 0);
-    parallel_for(N, [&](int64_t lo, int64_t hi) {
+    jf_parallel_for(N, [&](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; i++) {
-            auto a = raw.begin() + cnt[i], b = raw.begin() + cnt[i + 1];
-            std::sort(a, b);
-            ptr[i + 1] = std::unique(a, b) - a;
+            int32_t *a = &raw[4 * (size_t)iptr[i]], *w = a;
+            for (int32_t k = iptr[i]; k < iptr[i + 1]; k++) {
+                const int32_t *tt = &tets[4 * (int64_t)(isrc[k] >> 2)];
+                for (int r = 0; r < 4; r++) *w++ = tt[r];
+            }
+            std::sort(a, w);
+            ptr[i + 1] = std::unique(a, w) - a;
         }
     });
     for (int64_t i = 0; i < N; i++) ptr[i + 1] += ptr[i];
     adj.resize((size_t)ptr[N]);
-    for (int64_t i = 0; i < N; i++) std::copy(raw.begin() + cnt[i], raw.begin() + cnt[i] + (ptr[i + 1] - ptr[i]), adj.begin() + ptr[i]);
+    jf_parallel_for(N, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++)
+            std::copy(raw.begin() + 4 * (size_t)iptr[i], raw.begin() + 4 * (size_t)iptr[i] + (ptr[i + 1] - ptr[i]), adj.begin() + ptr[i]);
+    });
 }
 
 // Cost of the SpMV's vector gathers for a candidate ordering of the free nodes: the number of
@@ -167,29 +173,45 @@ static double gather_cost(const std::vector<int32_t> &order, int64_t N, const st
     const int64_t nf = (int64_t)order.size();
     std::vector<int32_t> o2n(N, -1);
     for (int64_t i = 0; i < nf; i++) o2n[order[i]] = (int32_t)i;
-    std::vector<int32_t> cols[JF_SLICE];
-    int32_t tmp[JF_SLICE];
+    const int64_t n_slices = (nf + JF_SLICE - 1) / JF_SLICE;
+    std::vector<double> part_lines(64, 0.0);
+    std::vector<int64_t> part_slots(64, 0);
+    std::atomic<int> part_id{0};
+    jf_parallel_for(n_slices, [&](int64_t sl_lo, int64_t sl_hi) {
+        std::vector<int32_t> cols[JF_SLICE];
+        int32_t tmp[JF_SLICE];
+        double lines = 0;
+        int64_t slots = 0;
+        for (int64_t sl = sl_lo; sl < sl_hi; sl++) {
+            const int64_t s0 = sl * JF_SLICE;
+            size_t w = 0;
+            const int nrow = (int)std::min<int64_t>(JF_SLICE, nf - s0);
+            for (int r = 0; r < nrow; r++) {
+                cols[r].clear();
+                const int32_t old = order[s0 + r];
+                for (int64_t k = ptr[old]; k < ptr[old + 1]; k++)
+                    if (o2n[adj[k]] >= 0) cols[r].push_back(o2n[adj[k]]);
+                std::sort(cols[r].begin(), cols[r].end());
+                w = std::max(w, cols[r].size());
+            }
+            slots += (int64_t)w * JF_SLICE;
+            for (size_t j = 0; j < w; j++) {
+                int n = 0;
+                for (int r = 0; r < nrow; r++)
+                    if (j < cols[r].size()) tmp[n++] = cols[r][j] >> 2;  // four 32-byte entries per line
+                std::sort(tmp, tmp + n);
+                lines += (double)(std::unique(tmp, tmp + n) - tmp);
+            }
+        }
+        const int id = part_id.fetch_add(1);
+        part_lines[id] = lines;
+        part_slots[id] = slots;
+    });
     double lines = 0;
     int64_t slots = 0;
-    for (int64_t s0 = 0; s0 < nf; s0 += JF_SLICE) {
-        size_t w = 0;
-        const int nrow = (int)std::min<int64_t>(JF_SLICE, nf - s0);
-        for (int r = 0; r < nrow; r++) {
-            cols[r].clear();
-            const int32_t old = order[s0 + r];
-            for (int64_t k = ptr[old]; k < ptr[old + 1]; k++)
-                if (o2n[adj[k]] >= 0) cols[r].push_back(o2n[adj[k]]);
-            std::sort(cols[r].begin(), cols[r].end());
-            w = std::max(w, cols[r].size());
-        }
-        slots += (int64_t)w * JF_SLICE;
-        for (size_t j = 0; j < w; j++) {
-            int n = 0;
-            for (int r = 0; r < nrow; r++)
-                if (j < cols[r].size()) tmp[n++] = cols[r][j] >> 2;  // four 32-byte entries per line
-            std::sort(tmp, tmp + n);
-            lines += (double)(std::unique(tmp, tmp + n) - tmp);
-        }
+    for (int i = 0; i < 64; i++) {
+        lines += part_lines[i];  // integer-valued: exact in any order
+        slots += part_slots[i];
     }
     if (slots_out) *slots_out = slots;
     return lines;
@@ -198,13 +220,16 @@ static double gather_cost(const std::vector<int32_t> &order, int64_t N, const st
 // Candidate orderings of the free nodes: the caller's order, and Cuthill-McKee (breadth-first,
 // neighbours by increasing degree); the one with the cheapest gathers wins.
 static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int64_t> &ptr,
-                        const std::vector<int32_t> &adj) {
+                        const std::vector<int32_t> &adj, StageTimer *tm = nullptr) {
     int64_t N = c->N;
     std::vector<int32_t> order;
     order.reserve(N);
     for (int64_t i = 0; i < N; i++)
         if (movable[i]) order.push_back((int32_t)i);
     if (!(c->flags & JF_FLAG_NO_REORDER)) {
+        int64_t slots_id = 0, slots_cm = 0;
+        double cost_id = 0, cost_cm = 0;
+        std::thread score_id([&] { cost_id = gather_cost(order, N, ptr, adj, &slots_id); });
         std::vector<int32_t> cm;
         cm.reserve(order.size());
         std::vector<int32_t> deg(N, 0);
@@ -235,13 +260,10 @@ static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int
                 cm.insert(cm.end(), nb.begin(), nb.end());
             }
         }
-        int64_t slots_id = 0, slots_cm = 0;
-        double cost_id = 0, cost_cm = 0;
-        {
-            std::thread other([&] { cost_cm = gather_cost(cm, N, ptr, adj, &slots_cm); });
-            cost_id = gather_cost(order, N, ptr, adj, &slots_id);
-            other.join();
-        }
+        if (tm) tm->mark("ordering: cuthill-mckee");
+        score_id.join();
+        cost_cm = gather_cost(cm, N, ptr, adj, &slots_cm);
+        if (tm) tm->mark("ordering: scores");
         // a gathered line and ~2 padded block slots cost about the same L1tex time
         if (cost_cm + 0.5 * (double)slots_cm / JF_SLICE < cost_id + 0.5 * (double)slots_id / JF_SLICE) order.swap(cm);
     }
@@ -257,6 +279,126 @@ template <typename Tp>
 static int upload(jf_ctx *c, Tp **dst, const std::vector<Tp> &src) {
     if (jf_dev_alloc(c, dst, src.size())) return JF_ERR_CUDA;
     if (!src.empty()) JF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    c->stats.bytes_h2d += (int64_t)(src.size() * sizeof(Tp));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// structure pieces built on the device (they are per-tet / per-row independent and were the longest host stages)
+// ------------------------------------------------------------------------------------------------
+// shape tensors Phi = Chi * B^-1, V = |det B|/6  (SURVEY A3); plain IEEE operations in the order of the CPU
+// restatement (no FMA contraction), first degenerate tet reported through *bad (old tet index, -1 if none)
+__global__ void __launch_bounds__(128) jf_shape_kernel(long long T, const int32_t *__restrict__ tets, const double *__restrict__ xyz,
+                                                       const int32_t *__restrict__ tet_new2old, double *__restrict__ phi,
+                                                       double *__restrict__ vol, int *__restrict__ bad) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int32_t *n = tets + 4 * t;
+    double B[3][3];
+    for (int col = 0; col < 3; col++)
+        for (int i = 0; i < 3; i++) B[i][col] = __dsub_rn(xyz[3ll * n[col + 1] + i], xyz[3ll * n[0] + i]);
+#define MUL(a, b) __dmul_rn(a, b)
+#define SUB(a, b) __dsub_rn(a, b)
+#define MINOR(a, b, c, d) SUB(MUL(a, b), MUL(c, d))
+    const double det = __dadd_rn(SUB(MUL(B[0][0], MINOR(B[1][1], B[2][2], B[1][2], B[2][1])), MUL(B[0][1], MINOR(B[1][0], B[2][2], B[1][2], B[2][0]))),
+                                 MUL(B[0][2], MINOR(B[1][0], B[2][1], B[1][1], B[2][0])));
+    if (det == 0.0 || !isfinite(det)) {
+        atomicMax(bad, (int)tet_new2old[t]);  // any one of them will do for the message
+        return;
+    }
+    double inv[3][3];
+    inv[0][0] = __ddiv_rn(MINOR(B[1][1], B[2][2], B[1][2], B[2][1]), det);
+    inv[0][1] = __ddiv_rn(MINOR(B[0][2], B[2][1], B[0][1], B[2][2]), det);
+    inv[0][2] = __ddiv_rn(MINOR(B[0][1], B[1][2], B[0][2], B[1][1]), det);
+    inv[1][0] = __ddiv_rn(MINOR(B[1][2], B[2][0], B[1][0], B[2][2]), det);
+    inv[1][1] = __ddiv_rn(MINOR(B[0][0], B[2][2], B[0][2], B[2][0]), det);
+    inv[1][2] = __ddiv_rn(MINOR(B[0][2], B[1][0], B[0][0], B[1][2]), det);
+    inv[2][0] = __ddiv_rn(MINOR(B[1][0], B[2][1], B[1][1], B[2][0]), det);
+    inv[2][1] = __ddiv_rn(MINOR(B[0][1], B[2][0], B[0][0], B[2][1]), det);
+    inv[2][2] = __ddiv_rn(MINOR(B[0][0], B[1][1], B[0][1], B[1][0]), det);
+#undef MINOR
+#undef SUB
+#undef MUL
+    vol[t] = __ddiv_rn(fabs(det), 6.0);
+    double *P = phi + 12 * t;
+    for (int j = 0; j < 3; j++) {
+        P[j] = -__dadd_rn(__dadd_rn(inv[0][j], inv[1][j]), inv[2][j]);
+        P[3 + j] = inv[0][j];
+        P[6 + j] = inv[1][j];
+        P[9 + j] = inv[2][j];
+    }
+}
+
+// Gather lists of the stiffness: slot <- ((t*10+pair)*2+transpose), ascending t (deterministic summation order).
+// One thread per free row a: its contributions come from its incident tets (the force gather list, ascending t*4+m);
+// the j-th block of the row lives in slot slice_ptr[a/32] + 32 j + a%32, touched by this thread only.
+// FILL = false counts into cnt[slot + 1]; FILL = true writes the sources at cur[slot]++ (cur starts as the prefix sum).
+template <bool FILL>
+__global__ void __launch_bounds__(128) jf_contrib_kernel(long long Nf, const int32_t *__restrict__ tets, const int32_t *__restrict__ fptr,
+                                                         const int32_t *__restrict__ fsrc, const int32_t *__restrict__ rptr,
+                                                         const int32_t *__restrict__ rcol, const int32_t *__restrict__ slice_ptr,
+                                                         int32_t *__restrict__ cnt_or_cur, int32_t *__restrict__ csrc) {
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= Nf) return;
+    const int pair_of[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+    const int32_t *cb = rcol + rptr[a];
+    const int w = rptr[a + 1] - rptr[a];
+    const long long base = (long long)slice_ptr[a / JF_SLICE] + a % JF_SLICE;
+    for (int32_t k = fptr[a]; k < fptr[a + 1]; k++) {
+        const long long t = fsrc[k] >> 2;
+        const int m = fsrc[k] & 3;
+        for (int r = 0; r < 4; r++) {
+            const int32_t b = tets[4 * t + r];
+            if (b >= Nf) continue;
+            int lo = 0, hi = w;  // lower_bound in the row's sorted block columns
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cb[mid] < b) lo = mid + 1; else hi = mid;
+            }
+            const long long slot = base + (long long)lo * JF_SLICE;
+            if (FILL) csrc[cnt_or_cur[slot]++] = (int32_t)(((t * 10 + pair_of[m][r]) << 1) | (m > r));
+            else cnt_or_cur[slot + 1]++;
+        }
+    }
+}
+
+// in-place inclusive prefix sum of n int32 values by one CTA (setup only)
+__global__ void __launch_bounds__(1024) jf_prefix_kernel(long long n, int32_t *__restrict__ v) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + threadIdx.x;
+        int incl = i < n ? v[i] : 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int x = warp_tot[lane];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += o;
+            }
+            warp_tot[lane] = x;
+        }
+        __syncthreads();
+        if (i < n) v[i] = carry + (warp ? warp_tot[warp - 1] : 0) + incl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_tot[31];
+        __syncthreads();
+    }
+}
+
+// stream-ordered upload (pageable source: staged before the call returns, ordered before later work on the stream)
+template <typename Tp>
+static int upload_async(jf_ctx *c, Tp **dst, const std::vector<Tp> &src) {
+    if (jf_dev_alloc(c, dst, src.size())) return JF_ERR_CUDA;
+    if (!src.empty()) JF_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice, c->stream));
     c->stats.bytes_h2d += (int64_t)(src.size() * sizeof(Tp));
     return 0;
 }
@@ -278,73 +420,56 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
     tm.mark("validate+dirtab");
     build_adjacency(N, T, tets_in, aptr, adj);
     tm.mark("adjacency");
-    order_nodes(c, movable, aptr, adj);
+    order_nodes(c, movable, aptr, adj, &tm);
     tm.mark("ordering");
     const int64_t Nf = c->Nf;
     const std::vector<int32_t> &o2n = c->node_old2new;
 
     // tets: renumber, order by smallest new node id (keeps U gathers and K_el reads local)
     std::vector<int32_t> torder(T);
-    std::iota(torder.begin(), torder.end(), 0);
     if (!(c->flags & JF_FLAG_NO_REORDER)) {
         std::vector<int32_t> key(T);
-        for (int64_t t = 0; t < T; t++) {
-            int32_t k = o2n[tets_in[4 * t]];
-            for (int m = 1; m < 4; m++) k = std::min(k, o2n[tets_in[4 * t + m]]);
-            key[t] = k;
-        }
-        std::stable_sort(torder.begin(), torder.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+        jf_parallel_for(T, [&](int64_t lo, int64_t hi) {
+            for (int64_t t = lo; t < hi; t++) {
+                int32_t k = o2n[tets_in[4 * t]];
+                for (int m = 1; m < 4; m++) k = std::min(k, o2n[tets_in[4 * t + m]]);
+                key[t] = k;
+            }
+        });
+        // stable counting sort (keys are node ids)
+        std::vector<int32_t> start(N + 1, 0);
+        for (int64_t t = 0; t < T; t++) start[key[t] + 1]++;
+        for (int64_t i = 0; i < N; i++) start[i + 1] += start[i];
+        for (int64_t t = 0; t < T; t++) torder[start[key[t]]++] = (int32_t)t;
+    } else {
+        std::iota(torder.begin(), torder.end(), 0);
     }
     c->tet_new2old = torder;
     std::vector<int32_t> tets((size_t)4 * T);
-    for (int64_t t = 0; t < T; t++)
-        for (int m = 0; m < 4; m++) tets[4 * t + m] = o2n[tets_in[4 * (int64_t)torder[t] + m]];
+    jf_parallel_for(T, [&](int64_t lo, int64_t hi) {
+        for (int64_t t = lo; t < hi; t++)
+            for (int m = 0; m < 4; m++) tets[4 * t + m] = o2n[tets_in[4 * (int64_t)torder[t] + m]];
+    });
     std::vector<double> xyz((size_t)3 * N);
     for (int64_t i = 0; i < N; i++)
         for (int k = 0; k < 3; k++) xyz[3 * i + k] = nodes[3 * (int64_t)c->node_new2old[i] + k];
 
     tm.mark("renumber tets");
-    // shape tensors Phi = Chi * B^-1, V = |det B|/6  
-    std::vector<double> phi((size_t)12 * T), vol(T);
-    std::vector<int64_t> bad_tet(1, -1);
-    parallel_for(T, [&](int64_t lo_t, int64_t hi_t) {
-    for (int64_t t = lo_t; t < hi_t; t++) {
-        const int32_t *n = &tets[4 * t];
-        double B[3][3];
-        for (int col = 0; col < 3; col++)
-            for (int i = 0; i < 3; i++) B[i][col] = xyz[3 * (int64_t)n[col + 1] + i] - xyz[3 * (int64_t)n[0] + i];
-        double det = B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[2][1]) - B[0][1] * (B[1][0] * B[2][2] - B[1][2] * B[2][0]) +
-                     B[0][2] * (B[1][0] * B[2][1] - B[1][1] * B[2][0]);
-        if (det == 0.0 || !isfinite(det)) {
-            bad_tet[0] = torder[t];  // any one of them will do for the message
-            continue;
-        }
-        double inv[3][3];
-        inv[0][0] = (B[1][1] * B[2][2] - B[1][2] * B[2][1]) / det;
-        inv[0][1] = (B[0][2] * B[2][1] - B[0][1] * B[2][2]) / det;
-        inv[0][2] = (B[0][1] * B[1][2] - B[0][2] * B[1][1]) / det;
-        inv[1][0] = (B[1][2] * B[2][0] - B[1][0] * B[2][2]) / det;
-        inv[1][1] = (B[0][0] * B[2][2] - B[0][2] * B[2][0]) / det;
-        inv[1][2] = (B[0][2] * B[1][0] - B[0][0] * B[1][2]) / det;
-        inv[2][0] = (B[1][0] * B[2][1] - B[1][1] * B[2][0]) / det;
-        inv[2][1] = (B[0][1] * B[2][0] - B[0][0] * B[2][1]) / det;
-        inv[2][2] = (B[0][0] * B[1][1] - B[0][1] * B[1][0]) / det;
-        vol[t] = fabs(det) / 6.0;
-        double *P = &phi[12 * t];
-        for (int j = 0; j < 3; j++) {
-            P[j] = -(inv[0][j] + inv[1][j] + inv[2][j]);
-            P[3 + j] = inv[0][j];
-            P[6 + j] = inv[1][j];
-            P[9 + j] = inv[2][j];
-        }
+    // shape tensors on the device while the host goes on with the sparsity pattern
+    int *d_bad = nullptr;
+    int32_t *d_torder = nullptr;
+    if ((rc = upload_async(c, &c->d_tets, tets))) return rc;
+    if ((rc = upload_async(c, &c->d_nodes, xyz))) return rc;
+    if ((rc = upload_async(c, &d_torder, torder))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_phi, (size_t)12 * T))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_vol, (size_t)T))) return rc;
+    if ((rc = jf_dev_alloc(c, &d_bad, 1))) return rc;
+    JF_CUDA(cudaMemsetAsync(d_bad, 0xff, sizeof(int), c->stream));  // -1
+    if (T > 0) {
+        jf_shape_kernel<<<(unsigned)((T + 127) / 128), 128, 0, c->stream>>>(T, c->d_tets, c->d_nodes, d_torder, c->d_phi, c->d_vol, d_bad);
+        JF_CUDA(cudaGetLastError());
     }
-    });
-    if (bad_tet[0] >= 0) {
-        jf_set_error("tetrahedron %d is degenerate (zero volume)", (int)bad_tet[0]);
-        return JF_ERR_ARG;
-    }
-
-    tm.mark("shape tensors");
+    tm.mark("shape tensors (device)");
     // SELL-32 pattern over free rows / free columns, in new numbering
     c->n_slices = (Nf + JF_SLICE - 1) / JF_SLICE;
     c->Nf_pad = c->n_slices * JF_SLICE;
@@ -389,68 +514,47 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
                 sell_col[slice_ptr[k] + j * JF_SLICE + lane] = col;
             }
     }
-    auto slot_of = [&](int32_t row, int32_t col) -> int64_t {
-        const int32_t *a = &rcol[rptr[row]], *b = &rcol[rptr[row + 1]];
-        const int32_t *hit = std::lower_bound(a, b, col);
-        return (int64_t)slice_ptr[row / JF_SLICE] + (hit - a) * JF_SLICE + row % JF_SLICE;
-    };
     tm.mark("SELL pattern");
-    // gather lists for the stiffness: slot <- ((t*10+pair)*2+transpose), ascending t
-    static const int pair_of[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+    // gather lists for nodal forces: node <- (t*4+m), ascending
+    std::vector<int32_t> fptr, fsrc;
+    build_incidence(N, T, tets.data(), fptr, fsrc);
+    tm.mark("force gather lists");
+    // gather lists for the stiffness on the device (jf_contrib_kernel): count, prefix sum, fill
     if ((int64_t)T * 20 > 2000000000LL) {
         jf_set_error("mesh too large for 32-bit element offsets");
         return JF_ERR_ARG;
     }
-    // slot of every (t, m, r) contribution, -1 if it touches a fixed node (parallel: independent lookups)
-    std::vector<int32_t> eslot((size_t)16 * T);
-    parallel_for(T, [&](int64_t lo, int64_t hi) {
-        for (int64_t t = lo; t < hi; t++)
-            for (int m = 0; m < 4; m++) {
-                const int32_t a = tets[4 * t + m];
-                for (int r = 0; r < 4; r++) {
-                    const int32_t b = tets[4 * t + r];
-                    eslot[16 * t + 4 * m + r] = (a < Nf && b < Nf) ? (int32_t)slot_of(a, b) : -1;
-                }
-            }
-    });
-    // counting sort by slot, ascending t within a slot (deterministic summation order)
-    std::vector<int32_t> cptr((size_t)c->n_slots + 1, 0);
-    for (int64_t e = 0; e < 16 * T; e++)
-        if (eslot[e] >= 0) cptr[eslot[e] + 1]++;
-    for (int64_t q = 0; q < c->n_slots; q++) cptr[q + 1] += cptr[q];
-    std::vector<int32_t> csrc((size_t)cptr[c->n_slots]);
-    {
-        std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
-        for (int64_t t = 0; t < T; t++)
-            for (int m = 0; m < 4; m++)
-                for (int r = 0; r < 4; r++) {
-                    const int32_t q = eslot[16 * t + 4 * m + r];
-                    if (q >= 0) csrc[fill[q]++] = (int32_t)(((t * 10 + pair_of[m][r]) << 1) | (m > r));
-                }
+    std::vector<int32_t> rptr32(rptr.begin(), rptr.end());
+    int32_t *d_rptr = nullptr, *d_rcol = nullptr, *d_cur = nullptr;
+    if ((rc = upload_async(c, &c->d_slice_ptr, slice_ptr))) return rc;
+    if ((rc = upload_async(c, &c->d_sell_col, sell_col))) return rc;
+    if ((rc = upload_async(c, &c->d_fn_ptr, fptr))) return rc;
+    if ((rc = upload_async(c, &c->d_fn_src, fsrc))) return rc;
+    if ((rc = upload_async(c, &d_rptr, rptr32))) return rc;
+    if ((rc = upload_async(c, &d_rcol, rcol))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_contrib_ptr, (size_t)c->n_slots + 1))) return rc;
+    if ((rc = jf_dev_alloc(c, &d_cur, (size_t)c->n_slots + 1))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_contrib_src, (size_t)16 * T))) return rc;  // upper bound: every (t, m, r) between free nodes
+    JF_CUDA(cudaMemsetAsync(c->d_contrib_ptr, 0, ((size_t)c->n_slots + 1) * sizeof(int32_t), c->stream));
+    if (Nf > 0) {
+        const unsigned grid_rows = (unsigned)((Nf + 127) / 128);
+        jf_contrib_kernel<false><<<grid_rows, 128, 0, c->stream>>>(Nf, c->d_tets, c->d_fn_ptr, c->d_fn_src, d_rptr, d_rcol, c->d_slice_ptr,
+                                                                   c->d_contrib_ptr, nullptr);
+        jf_prefix_kernel<<<1, 1024, 0, c->stream>>>((long long)c->n_slots + 1, c->d_contrib_ptr);
+        JF_CUDA(cudaMemcpyAsync(d_cur, c->d_contrib_ptr, ((size_t)c->n_slots + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+        jf_contrib_kernel<true><<<grid_rows, 128, 0, c->stream>>>(Nf, c->d_tets, c->d_fn_ptr, c->d_fn_src, d_rptr, d_rcol, c->d_slice_ptr, d_cur,
+                                                                  c->d_contrib_src);
+        JF_CUDA(cudaGetLastError());
     }
-    tm.mark("stiffness gather lists");
-    // gather lists for nodal forces: node <- (t*4+m)
-    std::vector<int32_t> fptr(N + 1, 0);
-    for (int64_t i = 0; i < 4 * T; i++) fptr[tets[i] + 1]++;
-    for (int64_t i = 0; i < N; i++) fptr[i + 1] += fptr[i];
-    std::vector<int32_t> fsrc((size_t)4 * T);
-    {
-        std::vector<int32_t> fill(fptr.begin(), fptr.end() - 1);
-        for (int64_t i = 0; i < 4 * T; i++) fsrc[fill[tets[i]]++] = (int32_t)i;
+    int bad_tet = -1;
+    JF_CUDA(cudaMemcpyAsync(&bad_tet, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    for (void *tmp_buf : {(void *)d_rptr, (void *)d_rcol, (void *)d_cur, (void *)d_bad, (void *)d_torder}) cudaFreeAsync(tmp_buf, c->stream);
+    if (bad_tet >= 0) {
+        jf_set_error("tetrahedron %d is degenerate (zero volume)", bad_tet);
+        return JF_ERR_ARG;
     }
-
-    tm.mark("force gather lists");
-    if ((rc = upload(c, &c->d_tets, tets))) return rc;
-    if ((rc = upload(c, &c->d_nodes, xyz))) return rc;
-    if ((rc = upload(c, &c->d_phi, phi))) return rc;
-    if ((rc = upload(c, &c->d_vol, vol))) return rc;
-    if ((rc = upload(c, &c->d_slice_ptr, slice_ptr))) return rc;
-    if ((rc = upload(c, &c->d_sell_col, sell_col))) return rc;
-    if ((rc = upload(c, &c->d_contrib_ptr, cptr))) return rc;
-    if ((rc = upload(c, &c->d_contrib_src, csrc))) return rc;
-    if ((rc = upload(c, &c->d_fn_ptr, fptr))) return rc;
-    if ((rc = upload(c, &c->d_fn_src, fsrc))) return rc;
-    tm.mark("uploads");
+    tm.mark("stiffness lists (device)");
     c->h_rowlen.resize(Nf);
     for (int64_t i = 0; i < Nf; i++) c->h_rowlen[i] = (int32_t)(rptr[i + 1] - rptr[i]);
     c->h_sell_col.swap(sell_col);
