@@ -217,10 +217,217 @@ static double gather_cost(const std::vector<int32_t> &order, int64_t N, const st
     return lines;
 }
 
+// ------------------------------------------------------------------------------------------------
+// adjacency and ordering scores on the device
+// ------------------------------------------------------------------------------------------------
+constexpr int ADJ_CAP = 128;  // distinct neighbours per node the device path handles (else: host path)
+
+__global__ void __launch_bounds__(256) jf_inc_count_kernel(long long n4, const int32_t *__restrict__ tets, int32_t *__restrict__ cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) atomicAdd(&cnt[tets[i] + 1], 1);
+}
+
+__global__ void __launch_bounds__(256) jf_inc_fill_kernel(long long n4, const int32_t *__restrict__ tets, int32_t *__restrict__ cur,
+                                                          int32_t *__restrict__ isrc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) isrc[atomicAdd(&cur[tets[i]], 1)] = (int32_t)i;  // order within a node is irrelevant: the consumer sorts
+}
+
+// neighbours of node i (itself included): corners of its incident tets, sorted, distinct.
+// FILL = false: nd[i + 1] = count; FILL = true: adj[aptr[i] ..] = list
+template <bool FILL>
+__global__ void __launch_bounds__(128) jf_adj_kernel(long long N, const int32_t *__restrict__ tets, const int32_t *__restrict__ iptr,
+                                                     const int32_t *__restrict__ isrc, int32_t *__restrict__ nd_or_aptr,
+                                                     int32_t *__restrict__ adj, int *__restrict__ overflow) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int32_t list[ADJ_CAP];
+    int n = 0;
+    for (int32_t k = iptr[i]; k < iptr[i + 1]; k++) {
+        const int32_t *tt = tets + 4ll * (isrc[k] >> 2);
+        for (int r = 0; r < 4; r++) {
+            const int32_t v = tt[r];
+            int lo = 0, hi = n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (list[mid] < v) lo = mid + 1; else hi = mid;
+            }
+            if (lo < n && list[lo] == v) continue;
+            if (n == ADJ_CAP) {
+                *overflow = 1;
+                continue;
+            }
+            for (int q = n; q > lo; q--) list[q] = list[q - 1];
+            list[lo] = v;
+            n++;
+        }
+    }
+    if (FILL) {
+        int32_t *out = adj + nd_or_aptr[i];
+        for (int q = 0; q < n; q++) out[q] = list[q];
+    } else {
+        nd_or_aptr[i + 1] = n;
+    }
+}
+
+// gather_cost on the device: one warp per slice of 32 rows of a candidate ordering; out[0] += distinct 128-byte
+// lines over all block columns, out[1] += padded slots.  Integer sums: the same numbers as the host function.
+__global__ void __launch_bounds__(128) jf_score_kernel(long long nf, const int32_t *__restrict__ order, const int32_t *__restrict__ o2n,
+                                                       const int32_t *__restrict__ aptr, const int32_t *__restrict__ adj,
+                                                       unsigned long long *__restrict__ out) {
+    const long long sl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (sl * JF_SLICE >= nf) return;
+    const long long row = sl * JF_SLICE + lane;
+    int32_t cols[ADJ_CAP];
+    int n = 0;
+    if (row < nf) {
+        const int32_t old = order[row];
+        for (int32_t k = aptr[old]; k < aptr[old + 1]; k++) {
+            const int32_t v = o2n[adj[k]];
+            if (v < 0) continue;
+            int q = n++;
+            for (; q > 0 && cols[q - 1] > v; q--) cols[q] = cols[q - 1];
+            cols[q] = v;
+        }
+    }
+    int w = n;
+    for (int d = 16; d > 0; d >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, d));
+    unsigned long long lines = 0;
+    for (int j = 0; j < w; j++) {
+        const bool valid = j < n;
+        const int key = valid ? (cols[j] >> 2) : -1 - lane;  // four 32-byte entries per line
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        const bool leader = lane == __ffs(m) - 1;
+        lines += __popc(__ballot_sync(0xffffffffu, leader && valid));
+    }
+    if (lane == 0) {
+        atomicAdd(&out[0], lines);
+        atomicAdd(&out[1], (unsigned long long)w * JF_SLICE);
+    }
+}
+
+// in-place inclusive prefix sum of n int32 values by one CTA (setup only)
+__global__ void __launch_bounds__(1024) jf_prefix_kernel(long long n, int32_t *__restrict__ v) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + threadIdx.x;
+        int incl = i < n ? v[i] : 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int x = warp_tot[lane];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += o;
+            }
+            warp_tot[lane] = x;
+        }
+        __syncthreads();
+        if (i < n) v[i] = carry + (warp ? warp_tot[warp - 1] : 0) + incl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_tot[31];
+        __syncthreads();
+    }
+}
+
+// temporaries of the device-side setup, released by the caller
+struct SetupDev {
+    int32_t *tets_in = nullptr, *aptr = nullptr, *adj = nullptr;
+    unsigned long long *score = nullptr;  // [4]: lines, slots of the caller's order; lines, slots of Cuthill-McKee
+    bool have = false;
+};
+
+// adjacency on the device; host copies in ptr/adj.  Returns 1 if done, 0 if the host path must be used, < 0 on error.
+static int build_adjacency_device(jf_ctx *c, int64_t N, int64_t T, const int32_t *tets, std::vector<int64_t> &ptr, std::vector<int32_t> &adj,
+                                  SetupDev &d) {
+    if (T < 1 || getenv("JF_HOST_SETUP")) return 0;
+    const long long n4 = 4 * T;
+    int32_t *iptr = nullptr, *cur = nullptr, *isrc = nullptr;
+    int *overflow = nullptr;
+    int rc;
+    if ((rc = jf_dev_alloc(c, &d.tets_in, (size_t)n4))) return rc;
+    if ((rc = jf_dev_alloc(c, &iptr, (size_t)N + 1))) return rc;
+    if ((rc = jf_dev_alloc(c, &cur, (size_t)N + 1))) return rc;
+    if ((rc = jf_dev_alloc(c, &isrc, (size_t)n4))) return rc;
+    if ((rc = jf_dev_alloc(c, &d.aptr, (size_t)N + 1))) return rc;
+    if ((rc = jf_dev_alloc(c, &overflow, 1))) return rc;
+    if ((rc = jf_dev_alloc(c, &d.score, 4))) return rc;
+    JF_CUDA(cudaMemcpyAsync(d.tets_in, tets, (size_t)n4 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    c->stats.bytes_h2d += (int64_t)((size_t)n4 * sizeof(int32_t));
+    JF_CUDA(cudaMemsetAsync(iptr, 0, ((size_t)N + 1) * sizeof(int32_t), c->stream));
+    JF_CUDA(cudaMemsetAsync(d.aptr, 0, ((size_t)N + 1) * sizeof(int32_t), c->stream));
+    JF_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), c->stream));
+    JF_CUDA(cudaMemsetAsync(d.score, 0, 4 * sizeof(unsigned long long), c->stream));
+    const unsigned g4 = (unsigned)((n4 + 255) / 256), gn = (unsigned)((N + 127) / 128);
+    jf_inc_count_kernel<<<g4, 256, 0, c->stream>>>(n4, d.tets_in, iptr);
+    jf_prefix_kernel<<<1, 1024, 0, c->stream>>>(N + 1, iptr);
+    JF_CUDA(cudaMemcpyAsync(cur, iptr, ((size_t)N + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    jf_inc_fill_kernel<<<g4, 256, 0, c->stream>>>(n4, d.tets_in, cur, isrc);
+    jf_adj_kernel<false><<<gn, 128, 0, c->stream>>>(N, d.tets_in, iptr, isrc, d.aptr, nullptr, overflow);
+    jf_prefix_kernel<<<1, 1024, 0, c->stream>>>(N + 1, d.aptr);
+    JF_CUDA(cudaGetLastError());
+    std::vector<int32_t> aptr32((size_t)N + 1);
+    int over = 0;
+    JF_CUDA(cudaMemcpyAsync(aptr32.data(), d.aptr, ((size_t)N + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    JF_CUDA(cudaMemcpyAsync(&over, overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    JF_CUDA(cudaStreamSynchronize(c->stream));
+    bool ok = !over;
+    if (ok) {
+        adj.resize((size_t)aptr32[N]);
+        if ((rc = jf_dev_alloc(c, &d.adj, adj.size()))) return rc;
+        jf_adj_kernel<true><<<gn, 128, 0, c->stream>>>(N, d.tets_in, iptr, isrc, d.aptr, d.adj, overflow);
+        JF_CUDA(cudaGetLastError());
+        JF_CUDA(cudaMemcpyAsync(adj.data(), d.adj, adj.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        JF_CUDA(cudaStreamSynchronize(c->stream));
+        c->stats.bytes_d2h += (int64_t)((adj.size() + aptr32.size()) * sizeof(int32_t));
+        ptr.assign(aptr32.begin(), aptr32.end());
+        d.have = true;
+    }
+    for (void *tmp_buf : {(void *)iptr, (void *)cur, (void *)isrc, (void *)overflow}) cudaFreeAsync(tmp_buf, c->stream);
+    return ok ? 1 : 0;
+}
+
+static void release_setup_dev(jf_ctx *c, SetupDev &d) {
+    for (void *tmp_buf : {(void *)d.tets_in, (void *)d.aptr, (void *)d.adj, (void *)d.score})
+        if (tmp_buf) cudaFreeAsync(tmp_buf, c->stream);
+    d = SetupDev();
+}
+
+// launch the scoring of one candidate ordering (slot 0: the caller's order, 1: Cuthill-McKee); temporaries are
+// stream-ordered, so they can be released right after the launch
+static int score_on_device(jf_ctx *c, SetupDev &d, int which, const std::vector<int32_t> &order, int64_t N) {
+    std::vector<int32_t> o2n((size_t)N, -1);
+    for (size_t i = 0; i < order.size(); i++) o2n[order[i]] = (int32_t)i;
+    int32_t *d_order = nullptr, *d_o2n = nullptr;
+    int rc;
+    if ((rc = jf_dev_alloc(c, &d_order, order.size()))) return rc;
+    if ((rc = jf_dev_alloc(c, &d_o2n, (size_t)N))) return rc;
+    JF_CUDA(cudaMemcpyAsync(d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    JF_CUDA(cudaMemcpyAsync(d_o2n, o2n.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    const long long nf = (long long)order.size();
+    const long long n_slices = (nf + JF_SLICE - 1) / JF_SLICE;
+    if (n_slices > 0) {
+        jf_score_kernel<<<(unsigned)((n_slices + 3) / 4), 128, 0, c->stream>>>(nf, d_order, d_o2n, d.aptr, d.adj, d.score + 2 * which);
+        JF_CUDA(cudaGetLastError());
+    }
+    cudaFreeAsync(d_order, c->stream);
+    cudaFreeAsync(d_o2n, c->stream);
+    return 0;
+}
+
 // Candidate orderings of the free nodes: the caller's order, and Cuthill-McKee (breadth-first,
 // neighbours by increasing degree); the one with the cheapest gathers wins.
-static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int64_t> &ptr,
-                        const std::vector<int32_t> &adj, StageTimer *tm = nullptr) {
+static int order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int64_t> &ptr,
+                       const std::vector<int32_t> &adj, SetupDev &dev, StageTimer *tm = nullptr) {
     int64_t N = c->N;
     std::vector<int32_t> order;
     order.reserve(N);
@@ -229,7 +436,14 @@ static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int
     if (!(c->flags & JF_FLAG_NO_REORDER)) {
         int64_t slots_id = 0, slots_cm = 0;
         double cost_id = 0, cost_cm = 0;
-        std::thread score_id([&] { cost_id = gather_cost(order, N, ptr, adj, &slots_id); });
+        // the caller's order is scored (device, or a host thread) while Cuthill-McKee is being built
+        std::thread score_id;
+        if (dev.have) {
+            int rc = score_on_device(c, dev, 0, order, N);
+            if (rc) return rc;
+        } else {
+            score_id = std::thread([&] { cost_id = gather_cost(order, N, ptr, adj, &slots_id); });
+        }
         std::vector<int32_t> cm;
         cm.reserve(order.size());
         std::vector<int32_t> deg(N, 0);
@@ -261,8 +475,20 @@ static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int
             }
         }
         if (tm) tm->mark("ordering: cuthill-mckee");
-        score_id.join();
-        cost_cm = gather_cost(cm, N, ptr, adj, &slots_cm);
+        if (dev.have) {
+            int rc = score_on_device(c, dev, 1, cm, N);
+            if (rc) return rc;
+            unsigned long long sc[4];
+            JF_CUDA(cudaMemcpyAsync(sc, dev.score, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+            JF_CUDA(cudaStreamSynchronize(c->stream));
+            cost_id = (double)sc[0];
+            slots_id = (int64_t)sc[1];
+            cost_cm = (double)sc[2];
+            slots_cm = (int64_t)sc[3];
+        } else {
+            score_id.join();
+            cost_cm = gather_cost(cm, N, ptr, adj, &slots_cm);
+        }
         if (tm) tm->mark("ordering: scores");
         // a gathered line and ~2 padded block slots cost about the same L1tex time
         if (cost_cm + 0.5 * (double)slots_cm / JF_SLICE < cost_id + 0.5 * (double)slots_id / JF_SLICE) order.swap(cm);
@@ -273,6 +499,7 @@ static void order_nodes(jf_ctx *c, const uint8_t *movable, const std::vector<int
     c->node_new2old = order;
     c->node_old2new.assign(N, 0);
     for (int64_t i = 0; i < N; i++) c->node_old2new[order[i]] = (int32_t)i;
+    return 0;
 }
 
 template <typename Tp>
@@ -362,38 +589,6 @@ __global__ void __launch_bounds__(128) jf_contrib_kernel(long long Nf, const int
     }
 }
 
-// in-place inclusive prefix sum of n int32 values by one CTA (setup only)
-__global__ void __launch_bounds__(1024) jf_prefix_kernel(long long n, int32_t *__restrict__ v) {
-    __shared__ int warp_tot[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < n; base += 1024) {
-        const long long i = base + threadIdx.x;
-        int incl = i < n ? v[i] : 0;
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int x = warp_tot[lane];
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= d) x += o;
-            }
-            warp_tot[lane] = x;
-        }
-        __syncthreads();
-        if (i < n) v[i] = carry + (warp ? warp_tot[warp - 1] : 0) + incl;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += warp_tot[31];
-        __syncthreads();
-    }
-}
-
 // stream-ordered upload (pageable source: staged before the call returns, ordered before later work on the stream)
 template <typename Tp>
 static int upload_async(jf_ctx *c, Tp **dst, const std::vector<Tp> &src) {
@@ -418,9 +613,14 @@ int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets_in, c
     std::vector<int64_t> aptr;
     std::vector<int32_t> adj;
     tm.mark("validate+dirtab");
-    build_adjacency(N, T, tets_in, aptr, adj);
-    tm.mark("adjacency");
-    order_nodes(c, movable, aptr, adj, &tm);
+    SetupDev dev;
+    rc = build_adjacency_device(c, N, T, tets_in, aptr, adj, dev);
+    if (rc < 0) return rc;
+    if (rc == 0) build_adjacency(N, T, tets_in, aptr, adj);
+    tm.mark(dev.have ? "adjacency (device)" : "adjacency (host)");
+    rc = order_nodes(c, movable, aptr, adj, dev, &tm);
+    release_setup_dev(c, dev);
+    if (rc) return rc;
     tm.mark("ordering");
     const int64_t Nf = c->Nf;
     const std::vector<int32_t> &o2n = c->node_old2new;

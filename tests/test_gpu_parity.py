@@ -253,6 +253,28 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
         assert np.linalg.norm(other[0] - res[4][0]) / np.linalg.norm(res[4][0]) < 5e-5
 
 
+def test_device_and_host_structure_build_agree(beams, monkeypatch):
+    """Adjacency, ordering scores, shape tensors and gather lists are built on the device; JF_HOST_SETUP=1 keeps the
+    adjacency and the scores on the host.  Same structure -> same arithmetic -> identical bits."""
+    from jointforces_b200 import _lib
+    c = make_case(0.3, 100.0)
+    res = []
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("JF_HOST_SETUP", "1")
+        else:
+            monkeypatch.delenv("JF_HOST_SETUP", raising=False)
+        with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams) as ctx:
+            ctx.set_material(*COLLAGEN12)
+            ctx.set_targets(c["f_target"])
+            ctx.set_displacements(np.zeros_like(c["coords"]))
+            relrec, cgit, n = ctx.relax(0.0033, 12, 0.01)
+            res.append((ctx.displacements(), cgit[0].copy(), ctx.info()))
+    assert res[0][2]["n_slots"] == res[1][2]["n_slots"] and res[0][2]["n_blocks"] == res[1][2]["n_blocks"]
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][0], res[1][0])
+
+
 @pytest.mark.parametrize("streamed", [False, True])
 def test_batch_of_two_systems(beams, streamed):
     """Two load cases in lockstep: small enough to be resident together (one CTA group per system), and through
