@@ -70,7 +70,7 @@ static void ctx_free(jf_ctx *c) {
     void *ptrs[] = {c->d_tets, c->d_nodes, c->d_phi, c->d_vol, c->d_dirtab, c->d_mat, c->d_state, c->d_U, c->d_ft, c->d_f,
                     c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_halo_ptr, c->d_halo_nodes, c->d_lcol, c->d_bin_ptr, c->d_bin_nodes, c->d_curve_scratch,
-                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_r1, c->d_Ap1, c->d_partial, c->d_sync};
+                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_r1, c->d_Ap1, c->d_partial, c->d_sync, c->d_red_partial, c->d_red_ticket};
     if (c->stream) {
         for (void *p : ptrs)
             if (p) cudaFreeAsync(p, c->stream);
@@ -162,7 +162,10 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         tm.mark("cg configure");
         if ((rc = jf_elem_configure(c))) break;
         if ((rc = jf_dev_alloc(c, &c->d_partial, 64 * S * (size_t)std::max(c->cg_grid, c->cg_fused_stream_grid)))) break;  // (2 parities, <= 8 replicas, <= 3 sums, S, grid)
-        if ((rc = jf_dev_alloc(c, &c->d_sync, 4 + 8 * S * (size_t)c->cg_grid))) break;  // counter + (2, S, grid) 16-byte slots
+        if ((rc = jf_dev_alloc(c, &c->d_sync, 4 + 8 * S * (size_t)c->cg_grid))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_red_partial, S * 32 * 3))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_red_ticket, S))) break;
+        cudaMemsetAsync(c->d_red_ticket, 0, S * sizeof(unsigned), c->stream);  // counter + (2, S, grid) 16-byte slots
         cudaMemset(c->d_U, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_U0, 0, S * N * 3 * sizeof(double));
         cudaMemset(c->d_ft, 0, S * N * 3 * sizeof(double));

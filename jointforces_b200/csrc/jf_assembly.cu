@@ -14,38 +14,29 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) jf_assemble_K_kernel(const int32_t *__restrict__ cptr, const int32_t *__restrict__ csrc,
+// One CTA per group of 32 slots (= the 288 values of one SELL column of a slice), nine threads per slot: thread
+// (slot, comp) adds component comp of the slot's element blocks in list order, so the nine lanes of a slot read one
+// contiguous 72-byte block per contribution; the 288 results leave through shared memory as one contiguous line.
+__global__ void __launch_bounds__(288) jf_assemble_K_kernel(const int32_t *__restrict__ cptr, const int32_t *__restrict__ csrc,
                                                             const double *__restrict__ Kel, double *__restrict__ val,
                                                             const jf_sys_state *__restrict__ state, long long n_slots,
                                                             long long T) {
     const int s = blockIdx.y;
     if (!state[s].active) return;
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_slots) return;
+    __shared__ double stage[288];
+    const int slot_local = threadIdx.x / 9, comp = threadIdx.x - 9 * slot_local;
+    const int comp_t = (comp % 3) * 3 + comp / 3;  // block stored for (r,m): K_mr = K_rm^T
+    const long long q = (long long)blockIdx.x * 32 + slot_local;
     const double *K = Kel + (long long)s * T * 90;
-    double acc[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) acc[i] = 0.0;
+    double acc = 0.0;
     const int beg = cptr[q], end = cptr[q + 1];
     for (int c = beg; c < end; c++) {
         const int src = csrc[c];
-        const double *kb = K + (long long)(src >> 1) * 9;
-        double v[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) v[i] = kb[i];
-        if (src & 1) {  // block stored for (r,m): K_mr = K_rm^T
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int l = 0; l < 3; l++) acc[3 * i + l] += v[3 * l + i];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 9; i++) acc[i] += v[i];
-        }
+        acc += K[(long long)(src >> 1) * 9 + ((src & 1) ? comp_t : comp)];
     }
-    double *out = val + (long long)s * n_slots * 9 + (q >> 5) * 288 + (q & 31);
-#pragma unroll
-    for (int i = 0; i < 9; i++) out[32 * i] = acc[i];
+    stage[32 * comp + slot_local] = acc;
+    __syncthreads();
+    val[(long long)s * n_slots * 9 + (long long)blockIdx.x * 288 + threadIdx.x] = stage[threadIdx.x];
 }
 
 // nodal forces f = gather of f_el (A10), and the CG right-hand side b = f - f_target on free nodes
@@ -77,29 +68,37 @@ __global__ void __launch_bounds__(256) jf_gather_f_kernel(const int32_t *__restr
     }
 }
 
-// fixed-order reductions: strain energy, |f - f_t|^2 and |f|^2 over free nodes.  One CTA per system.
-__global__ void __launch_bounds__(1024) jf_reduce_kernel(const double *__restrict__ Et, const double *__restrict__ f,
-                                                         const double *__restrict__ b, jf_sys_state *__restrict__ state,
-                                                         long long N, long long Nf, long long Nf_pad, long long T) {
-    const int s = blockIdx.x;
+// fixed-order reductions: strain energy, |f - f_t|^2 and |f|^2 over free nodes.  RED_CTAS CTAs per system take
+// fixed strided shares and publish partial sums; the CTA that arrives last (self-resetting ticket) adds them in
+// index order -- deterministic whatever the arrival order.
+constexpr int RED_CTAS = 32;
+constexpr int RED_THREADS = 256;
+
+__global__ void __launch_bounds__(RED_THREADS) jf_reduce_kernel(const double *__restrict__ Et, const double *__restrict__ f,
+                                                                const double *__restrict__ b, jf_sys_state *__restrict__ state,
+                                                                double *__restrict__ partial, unsigned *__restrict__ ticket, long long N,
+                                                                long long Nf, long long Nf_pad, long long T) {
+    const int s = blockIdx.y;
     if (!state[s].active) return;
-    __shared__ double sm[3][1024];
+    __shared__ double sm[3][RED_THREADS];
+    __shared__ bool last;
     double e = 0.0, r2 = 0.0, f2 = 0.0;
     const double *E = Et + (long long)s * T;
-    for (long long t = threadIdx.x; t < T; t += 1024) e += E[t];
+    const long long stride = (long long)RED_CTAS * RED_THREADS, first = (long long)blockIdx.x * RED_THREADS + threadIdx.x;
+    for (long long t = first; t < T; t += stride) e += E[t];
     const double *fs = f + (long long)s * N * 3;
-    const double *bs = b + (long long)s * Nf_pad * 4;
-    for (long long n = threadIdx.x; n < Nf; n += 1024) {
+    const double4 *bs = (const double4 *)(b + (long long)s * Nf_pad * 4);
+    for (long long n = first; n < Nf; n += stride) {
         const double x = fs[3 * n], y = fs[3 * n + 1], z = fs[3 * n + 2];
         f2 += x * x + y * y + z * z;
-        const double bx = bs[4 * n], by = bs[4 * n + 1], bz = bs[4 * n + 2];
-        r2 += bx * bx + by * by + bz * bz;
+        const double4 bv = bs[n];
+        r2 += bv.x * bv.x + bv.y * bv.y + bv.z * bv.z;
     }
     sm[0][threadIdx.x] = e;
     sm[1][threadIdx.x] = r2;
     sm[2][threadIdx.x] = f2;
     __syncthreads();
-    for (int w = 512; w > 0; w >>= 1) {
+    for (int w = RED_THREADS / 2; w > 0; w >>= 1) {
         if (threadIdx.x < w) {
             sm[0][threadIdx.x] += sm[0][threadIdx.x + w];
             sm[1][threadIdx.x] += sm[1][threadIdx.x + w];
@@ -107,10 +106,24 @@ __global__ void __launch_bounds__(1024) jf_reduce_kernel(const double *__restric
         }
         __syncthreads();
     }
+    double *mine = partial + ((long long)s * RED_CTAS + blockIdx.x) * 3;
     if (threadIdx.x == 0) {
-        state[s].energy = sm[0][0];
-        state[s].residual2 = sm[1][0];
-        state[s].force2 = sm[2][0];
+        mine[0] = sm[0][0];
+        mine[1] = sm[1][0];
+        mine[2] = sm[2][0];
+        __threadfence();
+        last = atomicInc(&ticket[s], RED_CTAS - 1) == RED_CTAS - 1;  // wraps to 0: ready for the next launch
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 3) {
+        const volatile double *p = partial + (long long)s * RED_CTAS * 3 + threadIdx.x;
+        double acc = 0.0;
+        for (int k = 0; k < RED_CTAS; k++) acc += p[3 * k];
+        if (threadIdx.x == 0) state[s].energy = acc;
+        if (threadIdx.x == 1) state[s].residual2 = acc;
+        if (threadIdx.x == 2) state[s].force2 = acc;
     }
 }
 
@@ -163,9 +176,9 @@ int jf_spmv_host(jf_ctx *c, int sys, const double *x, double *y) {
 }
 
 int jf_launch_assembly(jf_ctx *c) {
-    dim3 gk((unsigned)((c->n_slots + 255) / 256), (unsigned)c->n_sys);
+    dim3 gk((unsigned)(c->n_slots / 32), (unsigned)c->n_sys);  // n_slots is a multiple of 32 (SELL-32)
     if (c->n_slots > 0) {
-        jf_assemble_K_kernel<<<gk, 256, 0, c->stream>>>(c->d_contrib_ptr, c->d_contrib_src, c->d_Kel, c->d_val, c->d_state,
+        jf_assemble_K_kernel<<<gk, 288, 0, c->stream>>>(c->d_contrib_ptr, c->d_contrib_src, c->d_Kel, c->d_val, c->d_state,
                                                         c->n_slots, c->T);
         JF_CUDA(cudaGetLastError());
         c->stats.kernel_launches++;
@@ -174,7 +187,8 @@ int jf_launch_assembly(jf_ctx *c) {
     jf_gather_f_kernel<<<gf, 256, 0, c->stream>>>(c->d_fn_ptr, c->d_fn_src, c->d_fel, c->d_ft, c->d_f, c->d_b, c->d_state, c->N,
                                                   c->Nf, c->Nf_pad, c->T);
     JF_CUDA(cudaGetLastError());
-    jf_reduce_kernel<<<c->n_sys, 1024, 0, c->stream>>>(c->d_Et, c->d_f, c->d_b, c->d_state, c->N, c->Nf, c->Nf_pad, c->T);
+    jf_reduce_kernel<<<dim3(RED_CTAS, (unsigned)c->n_sys), RED_THREADS, 0, c->stream>>>(c->d_Et, c->d_f, c->d_b, c->d_state, c->d_red_partial,
+                                                                                      c->d_red_ticket, c->N, c->Nf, c->Nf_pad, c->T);
     JF_CUDA(cudaGetLastError());
     c->stats.kernel_launches += 2;
     return 0;

@@ -125,8 +125,8 @@ __device__ __forceinline__ void deformation_gradient(const double *Us, const int
     }
 }
 
-template <int L>
-__global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a) {
+template <int L, int UN = 2, int MB = 3>
+__global__ void __launch_bounds__(JF_ELEM_BLOCK, MB) jf_element_kernel(ElemArgs a) {
     extern __shared__ double2 tab[];
     const int ndp = a.n_dirs_pad;
     for (int i = threadIdx.x; i < (JF_NTAB / 2) * ndp; i += blockDim.x) tab[i] = a.dirtab[i];
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a
 #pragma unroll
         for (int i = 0; i < 15; i++) H[i] = 0.0;
 
-#pragma unroll 2
+#pragma unroll UN
         for (int b = sub; b < ndp; b += L) {
             const double2 t0 = tab[0 * ndp + b], t1 = tab[1 * ndp + b], t2 = tab[2 * ndp + b];
             double l2 = C[0] * t0.x;
@@ -278,11 +278,11 @@ __global__ void __launch_bounds__(JF_ELEM_BLOCK, 3) jf_element_kernel(ElemArgs a
 
 }  // namespace
 
-template <int L>
+template <int L, int UN = 2, int MB = 3>
 static int elem_configure_t(jf_ctx *c, size_t smem) {
-    JF_CUDA(cudaFuncSetAttribute(jf_element_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JF_CUDA(cudaFuncSetAttribute(jf_element_kernel<L, UN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_element_kernel<L>, JF_ELEM_BLOCK, smem));
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_element_kernel<L, UN, MB>, JF_ELEM_BLOCK, smem));
     if (per_sm < 1) per_sm = 1;
     c->elem_grid = c->sm_count * per_sm;
     return 0;
@@ -294,6 +294,17 @@ int jf_elem_configure(jf_ctx *c) {
     if (const char *e = getenv("JF_ELEM_LANES")) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) c->elem_lanes = v;
+    }
+    c->elem_variant = 0;
+    if (const char *e = getenv("JF_ELEM_VARIANT")) c->elem_variant = atoi(e);  // tuning experiments (4 lanes only)
+    if (c->elem_lanes == 4) switch (c->elem_variant) {
+        case 1: return elem_configure_t<4, 3, 3>(c, smem);
+        case 2: return elem_configure_t<4, 4, 3>(c, smem);
+        case 3: return elem_configure_t<4, 2, 2>(c, smem);
+        case 4: return elem_configure_t<4, 4, 2>(c, smem);
+        case 5: return elem_configure_t<4, 2, 4>(c, smem);
+        case 6: return elem_configure_t<4, 1, 4>(c, smem);
+        default: c->elem_variant = 0;
     }
     switch (c->elem_lanes) {
         case 1: return elem_configure_t<1>(c, smem);
@@ -324,7 +335,15 @@ int jf_launch_element(jf_ctx *c) {
     long long groups_per_block = JF_ELEM_BLOCK / c->elem_lanes;
     long long need = ((long long)c->n_sys * c->T + groups_per_block - 1) / groups_per_block;
     int grid = (int)(need < c->elem_grid ? (need > 0 ? need : 1) : c->elem_grid);
-    switch (c->elem_lanes) {
+    if (c->elem_lanes == 4 && c->elem_variant) switch (c->elem_variant) {
+        case 1: jf_element_kernel<4, 3, 3><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        case 2: jf_element_kernel<4, 4, 3><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        case 3: jf_element_kernel<4, 2, 2><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        case 4: jf_element_kernel<4, 4, 2><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        case 5: jf_element_kernel<4, 2, 4><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+        default: jf_element_kernel<4, 1, 4><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
+    }
+    else switch (c->elem_lanes) {
         case 1: jf_element_kernel<1><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
         case 2: jf_element_kernel<2><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;
         case 8: jf_element_kernel<8><<<grid, JF_ELEM_BLOCK, smem, c->stream>>>(a); break;

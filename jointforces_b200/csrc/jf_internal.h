@@ -125,9 +125,12 @@ struct jf_ctx {
     int cg_fused = 0, cg_fused_stream = 0, cg_fused_stream_grid = 0;
     size_t cg_fused_smem = 0;
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
+    double *d_red_partial = nullptr;   // (S, 32, 3) partial sums of jf_reduce_kernel
+    unsigned *d_red_ticket = nullptr;  // (S) arrival tickets of jf_reduce_kernel (self-resetting)
     unsigned int *d_sync = nullptr;    // sums-only barrier: counter (16 B) + (2, S, grid) 16-byte slots
     int cg_grid = 0, elem_grid = 0;
     int cg_stream_halo = 0, elem_lanes = JF_ELEM_LANES;
+    int elem_variant = 0;  // JF_ELEM_VARIANT: unroll / occupancy experiments of the element kernel (4 lanes)
     int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0, cg_hmax = 0, cg_ctas_per_sys = 0;
     int32_t *d_halo_ptr = nullptr, *d_halo_nodes = nullptr;
     // radial curve extraction (jf_curves.cu)
