@@ -37,8 +37,8 @@ struct jf_table {
     // scratch, grown on demand
     double *d_in = nullptr, *d_out = nullptr;
     size_t cap_in = 0, cap_out = 0;
-    int32_t *d_flag = nullptr, *d_pos = nullptr, *d_iaux = nullptr;
-    size_t cap_flag = 0, cap_iaux = 0;
+    int32_t *d_flag = nullptr;  // keep flags, compaction offsets and the kept count
+    size_t cap_flag = 0;
     double *d_frame = nullptr;
     size_t cap_frame = 0;
     int64_t launches = 0;
@@ -361,7 +361,7 @@ void jf_table_destroy(jf_table *t) {
     if (!t) return;
     cudaSetDevice(t->device);
     void *ptrs[] = {t->d_values, t->d_transform, t->d_bounds, t->d_simplices, t->d_bucket_ptr, t->d_bucket_tri, t->d_broad_ptr,
-                    t->d_broad_tri, t->d_in, t->d_out, t->d_flag, t->d_pos, t->d_iaux, t->d_frame};
+                    t->d_broad_tri, t->d_in, t->d_out, t->d_flag, t->d_frame};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (t->stream) cudaStreamDestroy(t->stream);
