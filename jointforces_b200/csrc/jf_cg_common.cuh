@@ -43,6 +43,7 @@ struct CgArgs {
     long long maxiter;
     double step;
     int apply_update;
+    int prefetch = 1;           // single-reduction kernel: request the halo Ap right after the barrier (JF_CG_NO_PREFETCH=1: off)
 };
 
 // one 32-byte vector entry with a single 256-bit load (LDG.E.256 on sm_100a): a gathered node costs

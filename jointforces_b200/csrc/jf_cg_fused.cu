@@ -45,8 +45,9 @@ struct FusedShared {
 
 // all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order.
 // After it the lane that owns system s's totals runs `update(s, t0, t1, t2)` before the CTA barrier.
-template <int NQ, int KMAX, typename F>
-__device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, F update) {
+// first half: publish the CTA's partial sums and pass the grid barrier
+template <int NQ>
+__device__ __forceinline__ double *fused_publish_sync(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch) {
     epoch++;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // F_REPLICAS copies of the partial table: CTA b reads copy b % F_REPLICAS, so a line has fewer simultaneous readers
@@ -60,6 +61,15 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
         if (lane < F_REPLICAS) part[lane * table + (size_t)v * gridDim.x + blockIdx.x] = x;
     }
     grid.sync();
+    return part;
+}
+
+// second half: every CTA adds the partial sums in the same order; the lane that owns system s's totals runs
+// `update(s, t0, t1, t2)` before the CTA barrier
+template <int NQ, int KMAX, typename F>
+__device__ __forceinline__ void fused_collect(const CgArgs &a, FusedShared &sh, const double *part, F update) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const size_t table = (size_t)3 * a.n_sys * gridDim.x;
     for (int s = warp; s < a.n_sys; s += nwarps) {
         // all loads of all sums in flight before the first shuffle (grid <= 32*KMAX CTAs: KMAX per lane and sum)
         double v[3][KMAX];
@@ -83,6 +93,13 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
         if (lane == 0) update(s, t[0], t[1], t[2]);
     }
     __syncthreads();
+}
+
+// all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order
+template <int NQ, int KMAX, typename F>
+__device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, F update) {
+    const double *part = fused_publish_sync<NQ>(a, grid, sh, epoch);
+    fused_collect<NQ, KMAX>(a, sh, part, update);
 }
 
 __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
@@ -177,6 +194,9 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
     int cur = 0;
+    double4 pre[F_HALO_BATCH];  // Ap of the previous iteration at this thread's first-round halo nodes (generation "-1": 0)
+#pragma unroll
+    for (int k = 0; k < F_HALO_BATCH; k++) pre[k] = make_double4(0.0, 0.0, 0.0, 0.0);
     for (long long it = 1; it <= a.maxiter; it++) {
         int all = 1;
         for (int q = 0; q < a.n_sys; q++) all &= sh.done[q];
@@ -188,13 +208,14 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             const double alpha = sh.alpha[s], beta = sh.beta[s];  // of the previous iteration (0, 0 for the first)
             const double4 *Ao = cur ? A_0 : A_1;  // Ap of the previous iteration
             double4 *An = cur ? A_1 : A_0;        // this iteration's
-            // ---- halo: r_j -= alpha Ap_j ; p_j = r_j + beta p_j, once per distinct block column, r and p kept here ----
+            // ---- halo: r_j -= alpha Ap_j ; p_j = r_j + beta p_j, once per distinct block column, r and p kept here.
+            // The first round's Ap_j were requested right after the barrier (below), while the sums were collected.
             for (int hb = threadIdx.x; hb < nh; hb += F_HALO_BATCH * blockDim.x) {
                 double4 av[F_HALO_BATCH];
 #pragma unroll
                 for (int k = 0; k < F_HALO_BATCH; k++) {
                     const int h = hb + k * blockDim.x;
-                    av[k] = ld_node(Ao + hn[h < nh ? h : hb]);
+                    av[k] = (hb == (int)threadIdx.x && a.prefetch) ? pre[k] : ld_node(Ao + hn[h < nh ? h : hb]);
                 }
 #pragma unroll
                 for (int k = 0; k < F_HALO_BATCH; k++) {
@@ -253,7 +274,17 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             sh.warp[2][s][warp] = a2;
         }
         TMARK(1);
-        fused_allreduce<3, 5>(a, grid, sh, epoch, [&](int ss, double pAp, double rAp, double ApAp) {
+        const double *part = fused_publish_sync<3>(a, grid, sh, epoch);
+        // the next iteration's first round of halo loads (this iteration's Ap) travels while the sums are collected
+        if (on && nh > 0 && a.prefetch) {
+            const double4 *An_c = cur ? A_1 : A_0;
+#pragma unroll
+            for (int k = 0; k < F_HALO_BATCH; k++) {
+                const int h = (int)threadIdx.x + k * (int)blockDim.x;
+                pre[k] = ld_node(An_c + hn[h < nh ? h : 0]);
+            }
+        }
+        fused_collect<3, 5>(a, sh, part, [&](int ss, double pAp, double rAp, double ApAp) {
             if (sh.done[ss]) return;
             const double rho = sh.rho[ss];
             const double alpha = rho / pAp;
@@ -569,6 +600,8 @@ int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
 }
 
 int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
+    static const int no_prefetch = getenv("JF_CG_NO_PREFETCH") != nullptr;
+    a.prefetch = !no_prefetch;
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;
