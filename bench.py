@@ -324,7 +324,8 @@ def main():
             "ms_element": st["ms_element"] / K, "ms_assembly": st["ms_assembly"] / K, "ms_cg": st["ms_cg"] / K,
             "wall_ms_per_step": wall * 1e3 / K,
         },
-        "roofline": {"bound": "hbm", "kernel": "jf_cg_fused_kernel" if info.get("cg_fused") else "jf_cg_regres_kernel" if info["cg_resident"] == 2 else
+        "roofline": {"bound": "hbm", "kernel": "jf_cg_fused_kernel" if info.get("cg_fused") == 1 else "jf_cg_fused_stream_kernel" if info.get("cg_fused") == 2 else
+                     "jf_cg_regres_kernel" if info["cg_resident"] == 2 else
                      ("jf_cg_resident_kernel" if info["cg_resident"] == 1 else
                       ("jf_cg_streamhalo_kernel" if info.get("cg_stream_halo") else "jf_cg_stream_kernel")), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": "of " + peak_kind,
