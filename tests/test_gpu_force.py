@@ -198,3 +198,36 @@ def test_random_scattered_table_against_scipy():
     assert np.max(np.abs(got[ok] - ref[ok])) < 1e-12
     assert np.array_equal(t(pts[:100, 0], pts[:100, 1]), vals[:100]) or np.max(np.abs(t(pts[:100, 0], pts[:100, 1]) - vals[:100])) < 1e-13
     t.close()
+
+
+def test_table_error_paths():
+    """Bad triangulations and arguments are refused with an error code and a message, never a crash."""
+    import ctypes as C
+    from jointforces_b200 import _lib
+    L = _lib.load()
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    vals = np.arange(4.0)
+    from scipy.spatial import Delaunay
+    tri = Delaunay(pts)
+    simp = np.ascontiguousarray(tri.simplices, dtype=np.int32)
+    trans = np.ascontiguousarray(tri.transform, dtype=np.float64)
+    nbr = np.ascontiguousarray(tri.neighbors, dtype=np.int32)
+    h = _lib._vp()
+    bad = simp.copy()
+    bad[0, 0] = 7                                                     # vertex outside the point set
+    assert L.jf_table_create(C.byref(h), 0, 4, pts, vals, len(simp), bad, trans, nbr) == -1
+    assert b"outside the point set" in L.jf_last_error()
+    assert L.jf_table_create(C.byref(h), 0, 2, pts[:2], vals[:2], len(simp), simp, trans, nbr) == -1     # fewer than 3 points
+    assert L.jf_table_create(C.byref(h), 99, 4, pts, vals, len(simp), simp, trans, nbr) == -1            # no such device
+    same_x = np.array([[0.0, 0.0], [0.0, 1.0], [0.0, 2.0]])
+    assert L.jf_table_create(C.byref(h), 0, 3, same_x, vals[:3], 1, np.zeros((1, 3), np.int32) + np.arange(3, dtype=np.int32),
+                             np.zeros((1, 3, 2)), -np.ones((1, 3), np.int32)) == -1
+    assert b"abscissa" in L.jf_last_error()
+    # a valid table: corners reproduce the values, the centre is their mean, outside is NaN
+    t = force.TableInterpolant(pts, vals)
+    assert np.array_equal(t(pts[:, 0], pts[:, 1]), vals)
+    assert abs(float(t(0.5, 0.5)) - 1.5) < 1e-15 and np.isnan(t(1.5, 0.5)) and np.isnan(t(np.nan, 0.5))
+    with pytest.raises(ValueError):
+        force.TableInterpolant(np.zeros((3, 3)), np.zeros(3))
+    t.close()
+    t.close()                                                          # idempotent
