@@ -409,6 +409,41 @@ def test_irregular_random_mesh_matches_oracle(beams):
     assert np.abs(f - ref["forces"]).max() < 1e-3 * np.abs(ref["forces"]).max()
 
 
+def test_hub_node_beyond_the_device_setup_capacity(beams, capfd, monkeypatch):
+    """A node with more than 128 distinct neighbours (a hub at the centre of a point cloud on a sphere): the
+    device-side adjacency declines and the host path builds the structure; results still follow the oracle."""
+    from scipy.spatial import Delaunay
+    from jointforces_b200 import _lib
+    from oracle import c_oracle
+    rng = np.random.default_rng(4)
+    v = rng.normal(size=(260, 3))
+    shell = v / np.linalg.norm(v, axis=1)[:, None] * 1e-3
+    pts = np.vstack([np.zeros((1, 3)), shell, shell * 2.0])           # hub, inner shell, outer (fixed) shell
+    tets = Delaunay(pts).simplices.astype(np.int32)
+    B = pts[tets[:, 1:]] - pts[tets[:, :1]]
+    vol = np.abs(np.linalg.det(B)) / 6
+    tets = tets[vol > 1e-3 * np.median(vol)]                       # drop hull slivers
+    assert len(np.unique(tets)) == len(pts)
+    hub_degree = len(np.unique(tets[np.any(tets == 0, axis=1)]))
+    assert hub_degree > 129                                          # more than ADJ_CAP neighbours incl. itself
+    movable = np.ones(len(pts), bool)
+    movable[261:] = False
+    ft = np.zeros_like(pts)
+    ft[1:261] = -shell / 1e-3 * 2e-7                                   # inner shell pulled towards the hub
+    mat = COLLAGEN12
+    ref = c_oracle.relax(pts, tets, movable, ft, np.zeros_like(pts), beams, mat, 0.0033, 15, 0.01, nthreads=1)
+    monkeypatch.setenv("JF_TIMING", "1")
+    with _lib.Context(pts, tets, movable, beams=beams) as ctx:
+        info = ctx.info()
+        ctx.set_material(*mat); ctx.set_targets(ft); ctx.set_displacements(np.zeros_like(pts))
+        relrec, cgit, n = ctx.relax(0.0033, 15, 0.01)
+        U = ctx.displacements()
+    assert "adjacency (host)" in capfd.readouterr().err
+    assert info["cg_wmax"] >= hub_degree - 1
+    assert n[0] == ref["n_iter"]
+    assert np.linalg.norm(U - ref["U"]) / np.linalg.norm(ref["U"]) < 1e-4
+
+
 def test_golden_oracle_table_rows(beams):
     """GPU curves against the committed oracle curves of the BatchA recipe at 1 Pa .. 10 kPa (1e-3, BASELINE tolerance)."""
     from jointforces_b200.sweep import relax_load_cases
