@@ -43,6 +43,7 @@ struct CgArgs {
     long long maxiter;
     double step;
     int apply_update;
+    int light_barrier = 1;      // single-reduction kernel: counter barrier without the L1 invalidation (JF_CG_CGSYNC=1: grid.sync)
     int prefetch = 1;           // single-reduction kernel: request the halo Ap right after the barrier (JF_CG_NO_PREFETCH=1: off)
 };
 
@@ -51,6 +52,14 @@ struct CgArgs {
 __device__ __forceinline__ double4 ld_node(const double4 *p) {
     double4 v;
     asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+
+// the same load served by L2 (never by this SM's L1): for data other CTAs wrote in this launch when the barrier in
+// between does not invalidate L1
+__device__ __forceinline__ double4 ld_node_l2(const double4 *p) {
+    double4 v;
+    asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
 

@@ -45,9 +45,28 @@ struct FusedShared {
 
 // all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order.
 // After it the lane that owns system s's totals runs `update(s, t0, t1, t2)` before the CTA barrier.
+// Grid barrier for the iteration loop: monotone arrival counter (zeroed before every launch), release fence before
+// the arrival, no L1 invalidation after it -- everything this kernel reads from other CTAs afterwards (halo Ap,
+// partial sums) is loaded from L2 (ld.global.cg), and nothing else it reads changes during the launch.
+// cg::grid.sync() adds MEMBAR + CCTL.IVALL on the way out (8 % of an iteration in the ncu source view).
+__device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        unsigned seen;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
 // first half: publish the CTA's partial sums and pass the grid barrier
-template <int NQ>
-__device__ __forceinline__ double *fused_publish_sync(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch) {
+template <int NQ, bool LIGHT = false>
+__device__ __forceinline__ double *fused_publish_sync(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch,
+                                                      unsigned *light_target = nullptr) {
     epoch++;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // F_REPLICAS copies of the partial table: CTA b reads copy b % F_REPLICAS, so a line has fewer simultaneous readers
@@ -60,7 +79,8 @@ __device__ __forceinline__ double *fused_publish_sync(const CgArgs &a, cg::grid_
         x = warp_sum(x);
         if (lane < F_REPLICAS) part[lane * table + (size_t)v * gridDim.x + blockIdx.x] = x;
     }
-    grid.sync();
+    if (LIGHT && a.light_barrier) light_grid_barrier(a.sync_ctr, *light_target);
+    else grid.sync();
     return part;
 }
 
@@ -194,6 +214,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
     int cur = 0;
+    unsigned light_target = 0;  // arrivals expected at the light barrier so far (thread 0)
     double4 pre[F_HALO_BATCH];  // Ap of the previous iteration at this thread's first-round halo nodes (generation "-1": 0)
 #pragma unroll
     for (int k = 0; k < F_HALO_BATCH; k++) pre[k] = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -215,7 +236,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
 #pragma unroll
                 for (int k = 0; k < F_HALO_BATCH; k++) {
                     const int h = hb + k * blockDim.x;
-                    av[k] = (hb == (int)threadIdx.x && a.prefetch) ? pre[k] : ld_node(Ao + hn[h < nh ? h : hb]);
+                    av[k] = (hb == (int)threadIdx.x && a.prefetch) ? pre[k] : ld_node_l2(Ao + hn[h < nh ? h : hb]);
                 }
 #pragma unroll
                 for (int k = 0; k < F_HALO_BATCH; k++) {
@@ -274,14 +295,14 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             sh.warp[2][s][warp] = a2;
         }
         TMARK(1);
-        const double *part = fused_publish_sync<3>(a, grid, sh, epoch);
+        const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
         // the next iteration's first round of halo loads (this iteration's Ap) travels while the sums are collected
         if (on && nh > 0 && a.prefetch) {
             const double4 *An_c = cur ? A_1 : A_0;
 #pragma unroll
             for (int k = 0; k < F_HALO_BATCH; k++) {
                 const int h = (int)threadIdx.x + k * (int)blockDim.x;
-                pre[k] = ld_node(An_c + hn[h < nh ? h : 0]);
+                pre[k] = ld_node_l2(An_c + hn[h < nh ? h : 0]);
             }
         }
         fused_collect<3, 5>(a, sh, part, [&](int ss, double pAp, double rAp, double ApAp) {
@@ -600,8 +621,9 @@ int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
 }
 
 int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
-    static const int no_prefetch = getenv("JF_CG_NO_PREFETCH") != nullptr;
+    static const int no_prefetch = getenv("JF_CG_NO_PREFETCH") != nullptr, cg_sync = getenv("JF_CG_CGSYNC") != nullptr;
     a.prefetch = !no_prefetch;
+    a.light_barrier = !cg_sync;
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;
