@@ -53,7 +53,7 @@ __device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &targ
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
+        __threadfence();  // (red.release.gpu compiles to the same MEMBAR + REDG sequence)
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned seen;
         do {
