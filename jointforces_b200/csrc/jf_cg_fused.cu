@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
         if (!sh.done[ss] && t0 == 0.0) sh.done[ss] = 1;
     });
 
+    unsigned light_target = 0;
     int cur = 0;
     for (long long it = 1; it <= a.maxiter; it++) {
         int all = 1;
@@ -447,9 +448,9 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
                         }
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
-                            rv[k] = ld_node(Ro + node[k]);
-                            av[k] = ld_node(Ao + node[k]);
-                            pv[k] = ld_node(Po + node[k]);
+                            rv[k] = ld_node_l2(Ro + node[k]);  // other CTAs' rows: from L2 (the loop's barrier keeps L1)
+                            av[k] = ld_node_l2(Ao + node[k]);
+                            pv[k] = ld_node_l2(Po + node[k]);
                         }
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
@@ -517,7 +518,8 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
                 sh.warp[2][s][warp] = a2;
             }
         }
-        fused_allreduce<3, 10>(a, grid, sh, epoch, [&](int ss, double pAp, double rAp, double ApAp) {
+        const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+        fused_collect<3, 10>(a, sh, part, [&](int ss, double pAp, double rAp, double ApAp) {
             if (sh.done[ss]) return;
             const double rho = sh.rho[ss];
             const double alpha = rho / pAp;
@@ -608,6 +610,8 @@ int jf_cg_fused_stream_configure(jf_ctx *c) {
 }
 
 int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
+    static const int cg_sync = getenv("JF_CG_CGSYNC") != nullptr;
+    a.light_barrier = !cg_sync;
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;
