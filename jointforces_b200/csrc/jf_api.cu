@@ -162,7 +162,8 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         tm.mark("cg configure");
         if ((rc = jf_elem_configure(c))) break;
         if ((rc = jf_dev_alloc(c, &c->d_partial, 64 * S * (size_t)std::max(c->cg_grid, c->cg_fused_stream_grid)))) break;  // (2 parities, <= 8 replicas, <= 3 sums, S, grid)
-        if ((rc = jf_dev_alloc(c, &c->d_sync, 4 + 8 * S * (size_t)c->cg_grid))) break;
+        // barrier counter (16 B), 3 x 8 fixed-point accumulators at byte 64, then (2, S, grid) 16-byte slots at byte 256
+        if ((rc = jf_dev_alloc(c, &c->d_sync, 64 + 8 * S * (size_t)c->cg_grid))) break;
         if ((rc = jf_dev_alloc(c, &c->d_red_partial, S * 32 * 3))) break;
         if ((rc = jf_dev_alloc(c, &c->d_red_ticket, S))) break;
         cudaMemsetAsync(c->d_red_ticket, 0, S * sizeof(unsigned), c->stream);  // counter + (2, S, grid) 16-byte slots

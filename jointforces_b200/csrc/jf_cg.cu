@@ -76,7 +76,7 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     // isolated micro-benchmark says the opposite: 1.6 vs 2.05 us) -- off unless JF_CG_SUMS_ONLY=1
     a.sums_only = getenv("JF_CG_SUMS_ONLY") ? atoi(getenv("JF_CG_SUMS_ONLY")) : 0;
     a.sync_ctr = c->d_sync;
-    a.sum_slots = (ulonglong2 *)(c->d_sync + 4);
+    a.sum_slots = (ulonglong2 *)(c->d_sync + 64);
     a.state = c->d_state;
     a.U = c->d_U;
     a.N = c->N;
@@ -91,7 +91,7 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     a.step = step;
     a.apply_update = apply_update;
     // counter and flag words of the sums-only barrier restart at zero in every launch (a few KB, same stream)
-    JF_CUDA(cudaMemsetAsync(c->d_sync, 0, 16 + (size_t)2 * c->n_sys * c->cg_grid * sizeof(ulonglong2), c->stream));
+    JF_CUDA(cudaMemsetAsync(c->d_sync, 0, 256 + (size_t)2 * c->n_sys * c->cg_grid * sizeof(ulonglong2), c->stream));
     // The single-reduction kernel carries r.r by recurrence; its absolute error (~4 eps times the sum of all earlier
     // r.r) is harmless at saenopy's tolerance of 1e-5 but makes the stop test meaningless below ~1e-12, so tight
     // tolerances go through the classic two-reduction kernels.

@@ -43,6 +43,8 @@ struct CgArgs {
     long long maxiter;
     double step;
     int apply_update;
+    unsigned long long *acc = nullptr;  // single-reduction kernel: 3 x 8 fixed-point accumulators (zeroed before every launch)
+    int exact_sums = 1;         // sums through integer atomics that double as the barrier (JF_CG_SLOT_SUMS=1: slot tables)
     int light_barrier = 1;      // single-reduction kernel: counter barrier without the L1 invalidation (JF_CG_CGSYNC=1: grid.sync)
     int prefetch = 1;           // single-reduction kernel: request the halo Ap right after the barrier (JF_CG_NO_PREFETCH=1: off)
 };

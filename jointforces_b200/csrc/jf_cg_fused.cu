@@ -41,6 +41,14 @@ struct FusedShared {
     double warp[3][F_MAX_SYS][8];  // per-warp partials of (p.Ap, r.Ap, Ap.Ap)
     double normb[F_MAX_SYS], rho[F_MAX_SYS], alpha[F_MAX_SYS], beta[F_MAX_SYS], tot0[F_MAX_SYS];
     int done[F_MAX_SYS], iters[F_MAX_SYS], lastcur[F_MAX_SYS];
+    // fixed-point all-reduce (one system): exponents of the previous iteration's p.Ap and Ap.Ap, words to add
+    int expo[2], scale_ok, fallback;
+    unsigned long long word[6];
+    int overflow[3];
+#ifdef JF_FX_CHECK
+    double dbg[3], dbg_max;
+    int dbg_n;
+#endif
 };
 
 // all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order.
@@ -61,6 +69,27 @@ __device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &targ
         } while (seen < target);
     }
     __syncthreads();
+}
+
+// ---- all-reduce through integer atomics that double as the grid barrier (one system) --------------------------
+// Each of the three sums is accumulated exactly as a 94-bit fixed-point number in two 64-bit words (47 bits each, the
+// high part biased to stay non-negative); every addend also adds 1 to the top byte of its word, so a word whose top
+// byte equals the number of CTAs is complete: arrival and data are the same atomic, and one poll of two sectors
+// replaces the barrier's poll plus the separate read of 3 x grid partial sums.  The unit is 2^-26 (high) and 2^-73
+// (low) of 2^E, E = exponent of the previous iteration's total (all CTAs derive it from the same bits), so a partial
+// may be 2^19 times larger than the previous total before it does not fit; such an iteration falls back to the slot
+// tables, which are always written too.  Integer addition is order independent: bitwise reproducible by construction.
+constexpr int FX_BITS = 47;
+constexpr int FX_HI_SHIFT = 26, FX_LO_SHIFT = FX_HI_SHIFT + FX_BITS;  // unit_hi = 2^(E-26), unit_lo = 2^(E-73)
+constexpr int FX_HEADROOM = 19;
+
+__device__ __forceinline__ double pow2(int k) { return __longlong_as_double((long long)(k + 1023) << 52); }  // -1022 <= k <= 1023
+
+__device__ __forceinline__ bool fx_exponent_ok(double v, int *e) {
+    if (!(v > 0.0) || !isfinite(v)) return false;
+    const int k = ilogb(v) + 1;
+    *e = k;
+    return k > -900 + FX_LO_SHIFT && k < 900 - FX_HEADROOM;
 }
 
 // first half: publish the CTA's partial sums and pass the grid barrier
@@ -149,6 +178,10 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
         sh.alpha[threadIdx.x] = 0.0;
         sh.beta[threadIdx.x] = 0.0;
     }
+    if (threadIdx.x == 0) sh.scale_ok = sh.fallback = 0;
+#ifdef JF_FX_CHECK
+    if (threadIdx.x == 0) { sh.dbg_max = 0.0; sh.dbg_n = 0; }
+#endif
     for (int i = threadIdx.x; i < 3 * F_MAX_SYS * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
     __syncthreads();
     const bool sys_on = !sh.done[s];
@@ -215,6 +248,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
 #endif
     int cur = 0;
     unsigned light_target = 0;  // arrivals expected at the light barrier so far (thread 0)
+    unsigned xe = 0;            // iterations reduced through the fixed-point accumulators so far
     double4 pre[F_HALO_BATCH];  // Ap of the previous iteration at this thread's first-round halo nodes (generation "-1": 0)
 #pragma unroll
     for (int k = 0; k < F_HALO_BATCH; k++) pre[k] = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -295,17 +329,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             sh.warp[2][s][warp] = a2;
         }
         TMARK(1);
-        const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
-        // the next iteration's first round of halo loads (this iteration's Ap) travels while the sums are collected
-        if (on && nh > 0 && a.prefetch) {
-            const double4 *An_c = cur ? A_1 : A_0;
-#pragma unroll
-            for (int k = 0; k < F_HALO_BATCH; k++) {
-                const int h = (int)threadIdx.x + k * (int)blockDim.x;
-                pre[k] = ld_node_l2(An_c + hn[h < nh ? h : 0]);
-            }
-        }
-        fused_collect<3, 5>(a, sh, part, [&](int ss, double pAp, double rAp, double ApAp) {
+        auto update = [&](int ss, double pAp, double rAp, double ApAp) {
             if (sh.done[ss]) return;
             const double rho = sh.rho[ss];
             const double alpha = rho / pAp;
@@ -318,7 +342,106 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 sh.beta[ss] = rsnew / rho;
                 sh.rho[ss] = rsnew;
             }
-        });
+            int e0 = 0, e2 = 0;  // units of the next iteration's fixed-point sums
+            const bool ok = fx_exponent_ok(pAp, &e0) & fx_exponent_ok(ApAp, &e2);
+            sh.expo[0] = e0;
+            sh.expo[1] = e2;
+            sh.scale_ok = ok;
+        };
+        auto prefetch_halo = [&]() {
+            // the next iteration's first round of halo loads (this iteration's Ap) travels while the scalars are formed
+            if (on && nh > 0 && a.prefetch) {
+                const double4 *An_c = cur ? A_1 : A_0;
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++) {
+                    const int h = (int)threadIdx.x + k * (int)blockDim.x;
+                    pre[k] = ld_node_l2(An_c + hn[h < nh ? h : 0]);
+                }
+            }
+        };
+        if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {  // the same decision in every CTA: scale_ok comes from shared totals
+            epoch++;
+            xe++;
+            const int nwarps = blockDim.x >> 5;
+            const size_t table = (size_t)3 * gridDim.x;
+            double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
+            unsigned long long *acc = a.acc + (xe % 3u) * 8;
+            __syncthreads();
+            for (int q = warp; q < 3; q += nwarps) {  // (a CTA of a small mesh may have two warps only)
+                double x = lane < nwarps ? sh.warp[q][0][lane] : 0.0;
+                x = warp_sum(x);
+                if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;  // for the fallback
+                if (lane == 0) {
+                    const int E = sh.expo[q == 2 ? 1 : 0];
+                    const bool ok = fabs(x) < pow2(E + FX_HEADROOM);  // false for NaN
+                    long long hi = 0, lo = 0;
+                    if (ok) {
+                        hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
+                        const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi), exact
+                        lo = __double2ll_rd(rem * pow2(FX_LO_SHIFT - E));
+                        lo = min(max(lo, 0ll), (1ll << FX_BITS) - 1);
+                    }
+                    sh.word[2 * q] = (1ull << 56) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
+                    sh.word[2 * q + 1] = (1ull << 56) + (unsigned long long)lo;
+                    sh.overflow[q] = !ok;
+                }
+            }
+            __syncthreads();
+            unsigned long long w = 0;  // warp 0, lanes 0..6: the accumulator words (6: partials that did not fit)
+            if (warp == 0) {
+                if (lane == 0) {
+                    if (sh.overflow[0] | sh.overflow[1] | sh.overflow[2])
+                        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + 6), "l"(1ull) : "memory");
+                    __threadfence();  // this CTA's Ap rows, fallback partials and the overflow mark are in L2 before it arrives
+                }
+                __syncwarp();
+                if (lane < 6) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(sh.word[lane]) : "memory");
+                bool complete;
+                do {
+                    // words 4, 5 and the overflow word share a sector: a poll that sees them complete sees every mark
+                    if (lane < 7) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(acc + lane) : "memory");
+                    complete = lane >= 6 || (unsigned)(w >> 56) == gridDim.x;
+                } while (!__all_sync(0xffffffffu, complete));
+                sh.fallback = 0;
+            }
+            __syncthreads();  // the barrier proper: every CTA's words are in
+            prefetch_halo();
+            if (warp == 0) {
+                if (blockIdx.x == 0 && lane < 7) a.acc[((xe + 2u) % 3u) * 8 + lane] = 0ull;  // recycle the buffer of the epoch before
+                double d = 0.0;
+                if (lane < 6) {
+                    const unsigned long long body = w & ((1ull << 56) - 1);
+                    const int E = sh.expo[(lane >> 1) == 2 ? 1 : 0];
+                    if (lane & 1) d = (double)body * pow2(E - FX_LO_SHIFT);
+                    else d = (double)((long long)body - (long long)gridDim.x * (1ll << (FX_BITS - 1))) * pow2(E - FX_HI_SHIFT);
+                }
+                const double t = d + __shfl_down_sync(0xffffffffu, d, 1);  // lanes 0, 2, 4: high + low part
+                const double t1 = __shfl_sync(0xffffffffu, t, 2), t2 = __shfl_sync(0xffffffffu, t, 4);
+                const unsigned long long ovf = __shfl_sync(0xffffffffu, w, 6);
+                if (lane == 0) {
+                    if (ovf) sh.fallback = 1;
+                    else update(0, t, t1, t2);
+#ifdef JF_FX_CHECK
+                    sh.dbg[0] = t; sh.dbg[1] = t1; sh.dbg[2] = t2;
+#endif
+                }
+            }
+            __syncthreads();
+            if (sh.fallback) fused_collect<3, 5>(a, sh, part, update);  // some partial did not fit: the slot tables have it
+#ifdef JF_FX_CHECK
+            else {  // debug build: the fixed-point totals against the slot-table sums of the same partials
+                fused_collect<3, 5>(a, sh, part, [&](int, double s0, double s1, double s2) {
+                    const double r0 = fabs(sh.dbg[0] - s0) / fabs(s0), r1 = fabs(sh.dbg[1] - s1) / fabs(s1), r2 = fabs(sh.dbg[2] - s2) / fabs(s2);
+                    sh.dbg_max = fmax(sh.dbg_max, fmax(r0, fmax(r1, r2)));
+                    sh.dbg_n++;
+                });
+            }
+#endif
+        } else {
+            const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+            prefetch_halo();
+            fused_collect<3, 5>(a, sh, part, update);
+        }
         TMARK(2);
         cur ^= 1;
     }
@@ -328,6 +451,9 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                (double)tacc[1] / sh.iters[0], (double)tacc[2] / sh.iters[0], nh);
 #endif
 
+#ifdef JF_FX_CHECK
+    if (threadIdx.x == 0 && blockIdx.x == 0) printf("fx-check: %d fixed-point reductions of %d iterations, max rel diff to slot sums %.3e\n", sh.dbg_n, sh.iters[0], sh.dbg_max);
+#endif
     // the last iteration's x += alpha p, then (A12) U[free] += step * x ; du = step^2 * sum x^2
     acc = 0.0;
     if (have && a.state[s].active) {
@@ -610,8 +736,7 @@ int jf_cg_fused_stream_configure(jf_ctx *c) {
 }
 
 int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
-    static const int cg_sync = getenv("JF_CG_CGSYNC") != nullptr;
-    a.light_barrier = !cg_sync;
+    a.light_barrier = getenv("JF_CG_CGSYNC") == nullptr;
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;
@@ -625,9 +750,13 @@ int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
 }
 
 int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
-    static const int no_prefetch = getenv("JF_CG_NO_PREFETCH") != nullptr, cg_sync = getenv("JF_CG_CGSYNC") != nullptr;
+    // read per launch (one CG solve = hundreds of iterations): tests switch them within a process
+    const bool no_prefetch = getenv("JF_CG_NO_PREFETCH") != nullptr, cg_sync = getenv("JF_CG_CGSYNC") != nullptr,
+               slot_sums = getenv("JF_CG_SLOT_SUMS") != nullptr;
     a.prefetch = !no_prefetch;
     a.light_barrier = !cg_sync;
+    a.exact_sums = !slot_sums && !cg_sync;
+    a.acc = (unsigned long long *)((char *)c->d_sync + 64);
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;

@@ -127,7 +127,7 @@ struct jf_ctx {
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
     double *d_red_partial = nullptr;   // (S, 32, 3) partial sums of jf_reduce_kernel
     unsigned *d_red_ticket = nullptr;  // (S) arrival tickets of jf_reduce_kernel (self-resetting)
-    unsigned int *d_sync = nullptr;    // sums-only barrier: counter (16 B) + (2, S, grid) 16-byte slots
+    unsigned int *d_sync = nullptr;    // barrier counter (16 B), fixed-point accumulators (byte 64), sums-only slots (byte 256)
     int cg_grid = 0, elem_grid = 0;
     int cg_stream_halo = 0, elem_lanes = JF_ELEM_LANES;
     int elem_variant = 0;  // JF_ELEM_VARIANT: unroll / occupancy experiments of the element kernel (4 lanes)

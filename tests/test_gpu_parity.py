@@ -144,13 +144,23 @@ def test_relaxation_tight_cg_matches_oracle_closely(beams):
     assert np.linalg.norm(U - m.displacements) / np.linalg.norm(U) < 1e-8
 
 
-def test_lockstep_batch_equals_single_solves(beams):
+def test_lockstep_batch_equals_single_solves(beams, monkeypatch):
+    """Three load cases in one lockstep batch against three single solves.  With the same reduction (slot tables,
+    JF_CG_SLOT_SUMS=1) the arithmetic is the same per system: identical bits.  By default a single system reduces
+    its CG sums through the fixed-point accumulators (exact sums, one rounding), a batch through the slot tables
+    (sequential double sums): agreement to the trajectory noise floor (DESIGN.md "Trajectory sensitivity")."""
     from jointforces_b200 import _lib
     pressures = [1.0, 100.0, 3000.0]
     cases = [make_case(0.667, p) for p in pressures]
     c0 = cases[0]
-    singles = [_lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
-                                            COLLAGEN12, 0.0033, 600, 0.01, beams=beams) for c in cases]
+
+    def run_singles():
+        return [_lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
+                                             COLLAGEN12, 0.0033, 600, 0.01, beams=beams) for c in cases]
+    singles = run_singles()
+    monkeypatch.setenv("JF_CG_SLOT_SUMS", "1")
+    singles_slot = run_singles()
+    monkeypatch.delenv("JF_CG_SLOT_SUMS")
     with _lib.Context(c0["coords"], c0["tets"], c0["movable"], n_sys=3, beams=beams) as ctx:
         ctx.set_material(*COLLAGEN12)
         for s, c in enumerate(cases):
@@ -158,9 +168,11 @@ def test_lockstep_batch_equals_single_solves(beams):
             ctx.set_displacements(np.zeros_like(c["coords"]), s)
         relrec, cgit, n = ctx.relax(0.0033, 600, 0.01)
         for s in range(3):
+            assert n[s] == singles_slot[s]["n_iter"]
+            assert np.array_equal(ctx.displacements(s), singles_slot[s]["U"])  # same kernels, same order: bitwise
+            assert np.array_equal(relrec[s], singles_slot[s]["relrec"])
             assert n[s] == singles[s]["n_iter"]
-            assert np.array_equal(ctx.displacements(s), singles[s]["U"])  # same kernels, same order: bitwise
-            assert np.array_equal(relrec[s], singles[s]["relrec"])
+            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < 5e-5
 
 
 def test_bitwise_reproducible(beams):
@@ -276,13 +288,19 @@ def test_device_and_host_structure_build_agree(beams, monkeypatch):
 
 
 @pytest.mark.parametrize("streamed", [False, True])
-def test_batch_of_two_systems(beams, streamed):
+def test_batch_of_two_systems(beams, streamed, monkeypatch):
     """Two load cases in lockstep: small enough to be resident together (one CTA group per system), and through
     the streaming kernels (systems finish their CG solves at different iterations)."""
     from jointforces_b200 import _lib
     cases = [make_case(0.667, p) for p in (10.0, 1000.0)]
-    singles = [_lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
-                                            COLLAGEN12, 0.0033, 30, 0.01, beams=beams) for c in cases]
+
+    def run_singles():
+        return [_lib.solve_boundarycondition(c["coords"], c["tets"], c["movable"], c["f_target"], np.zeros_like(c["coords"]),
+                                             COLLAGEN12, 0.0033, 30, 0.01, beams=beams) for c in cases]
+    monkeypatch.setenv("JF_CG_SLOT_SUMS", "1")       # the batch reduces through the slot tables: compare like with like
+    singles = run_singles()
+    monkeypatch.delenv("JF_CG_SLOT_SUMS")
+    singles_fx = run_singles()                        # default: fixed-point accumulators (exact sums)
     c0 = cases[0]
     with _lib.Context(c0["coords"], c0["tets"], c0["movable"], n_sys=2, beams=beams,
                       flags=_lib.JF_FLAG_NO_RESIDENT if streamed else 0) as ctx:
@@ -300,6 +318,10 @@ def test_batch_of_two_systems(beams, streamed):
             # rounding-sensitive, DESIGN.md "Trajectory sensitivity")
             assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= (0.15 * singles[s]["cg_iters"].max() if streamed else 2)
             assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < (5e-5 if streamed else 2e-5)
+            # thirty early-stopped, unconverged steps after a differently rounded reduction: the noise floor of such
+            # iterates is a few 1e-4 (1.7e-4 measured); it shrinks as the relaxation converges (5e-5 at the stop rule,
+            # test_lockstep_batch_equals_single_solves)
+            assert np.linalg.norm(ctx.displacements(s) - singles_fx[s]["U"]) / np.linalg.norm(singles_fx[s]["U"]) < 5e-4
 
 
 # ---- edge cases and error behaviour -----------------------------------------------------------------------
