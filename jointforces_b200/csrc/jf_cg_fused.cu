@@ -72,16 +72,17 @@ __device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &targ
 }
 
 // ---- all-reduce through integer atomics that double as the grid barrier (one system) --------------------------
-// Each of the three sums is accumulated exactly as a 94-bit fixed-point number in two 64-bit words (47 bits each, the
-// high part biased to stay non-negative); every addend also adds 1 to the top byte of its word, so a word whose top
-// byte equals the number of CTAs is complete: arrival and data are the same atomic, and one poll of two sectors
-// replaces the barrier's poll plus the separate read of 3 x grid partial sums.  The unit is 2^-26 (high) and 2^-73
+// Each of the three sums is accumulated exactly as an 88-bit fixed-point number in two 64-bit words (44 bits each, the
+// high part biased to stay non-negative); every addend also adds 1 to the top ten bits of its word, so a word whose
+// top bits equal the number of CTAs is complete: arrival and data are the same atomic, and one poll of two sectors
+// replaces the barrier's poll plus the separate read of 3 x grid partial sums.  The unit is 2^-23 (high) and 2^-67
 // (low) of 2^E, E = exponent of the previous iteration's total (all CTAs derive it from the same bits), so a partial
 // may be 2^19 times larger than the previous total before it does not fit; such an iteration falls back to the slot
 // tables, which are always written too.  Integer addition is order independent: bitwise reproducible by construction.
-constexpr int FX_BITS = 47;
-constexpr int FX_HI_SHIFT = 26, FX_LO_SHIFT = FX_HI_SHIFT + FX_BITS;  // unit_hi = 2^(E-26), unit_lo = 2^(E-73)
+constexpr int FX_COUNT_SHIFT = 54;  // arrivals in the top 10 bits: grids of up to 1023 CTAs
+constexpr int FX_BITS = 44;         // bits per limb: 1023 biased limbs stay below 2^54
 constexpr int FX_HEADROOM = 19;
+constexpr int FX_HI_SHIFT = FX_BITS - 2 - FX_HEADROOM, FX_LO_SHIFT = FX_HI_SHIFT + FX_BITS;  // unit_hi = 2^(E-23), unit_lo = 2^(E-67)
 
 __device__ __forceinline__ double pow2(int k) { return __longlong_as_double((long long)(k + 1023) << 52); }  // -1022 <= k <= 1023
 
@@ -149,6 +150,90 @@ template <int NQ, int KMAX, typename F>
 __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, F update) {
     const double *part = fused_publish_sync<NQ>(a, grid, sh, epoch);
     fused_collect<NQ, KMAX>(a, sh, part, update);
+}
+
+// The fixed-point all-reduce as a function (streaming kernel; the register-resident kernel has the same statements
+// inline).  `after_barrier` runs in every thread once all CTAs have arrived, before the scalars are formed.
+template <int KMAX, typename U, typename P>
+__device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared &sh, unsigned &epoch, unsigned &xe, U update, P after_barrier) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    epoch++;
+    xe++;
+    const int nwarps = blockDim.x >> 5;
+    const size_t table = (size_t)3 * gridDim.x;
+    double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
+    unsigned long long *acc = a.acc + (xe % 3u) * 8;
+    __syncthreads();
+    for (int q = warp; q < 3; q += nwarps) {  // (a CTA of a small mesh may have two warps only)
+        double x = lane < nwarps ? sh.warp[q][0][lane] : 0.0;
+        x = warp_sum(x);
+        if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;  // for the fallback
+        if (lane == 0) {
+            const int E = sh.expo[q == 2 ? 1 : 0];
+            const bool ok = fabs(x) < pow2(E + FX_HEADROOM);  // false for NaN
+            long long hi = 0, lo = 0;
+            if (ok) {
+                hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
+                const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi), exact
+                lo = __double2ll_rd(rem * pow2(FX_LO_SHIFT - E));
+                lo = min(max(lo, 0ll), (1ll << FX_BITS) - 1);
+            }
+            sh.word[2 * q] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
+            sh.word[2 * q + 1] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)lo;
+            sh.overflow[q] = !ok;
+        }
+    }
+    __syncthreads();
+    unsigned long long w = 0;  // warp 0, lanes 0..6: the accumulator words (6: partials that did not fit)
+    if (warp == 0) {
+        if (lane == 0) {
+            if (sh.overflow[0] | sh.overflow[1] | sh.overflow[2])
+                asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + 6), "l"(1ull) : "memory");
+            __threadfence();  // this CTA's Ap rows, fallback partials and the overflow mark are in L2 before it arrives
+        }
+        __syncwarp();
+        if (lane < 6) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(sh.word[lane]) : "memory");
+        bool complete;
+        do {
+            // words 4, 5 and the overflow word share a sector: a poll that sees them complete sees every mark
+            if (lane < 7) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(acc + lane) : "memory");
+            complete = lane >= 6 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
+        } while (!__all_sync(0xffffffffu, complete));
+        sh.fallback = 0;
+    }
+    __syncthreads();  // the barrier proper: every CTA's words are in
+    after_barrier();
+    if (warp == 0) {
+        if (blockIdx.x == 0 && lane < 7) a.acc[((xe + 2u) % 3u) * 8 + lane] = 0ull;  // recycle the buffer of the epoch before
+        double d = 0.0;
+        if (lane < 6) {
+            const unsigned long long body = w & ((1ull << FX_COUNT_SHIFT) - 1);
+            const int E = sh.expo[(lane >> 1) == 2 ? 1 : 0];
+            if (lane & 1) d = (double)body * pow2(E - FX_LO_SHIFT);
+            else d = (double)((long long)body - (long long)gridDim.x * (1ll << (FX_BITS - 1))) * pow2(E - FX_HI_SHIFT);
+        }
+        const double t = d + __shfl_down_sync(0xffffffffu, d, 1);  // lanes 0, 2, 4: high + low part
+        const double t1 = __shfl_sync(0xffffffffu, t, 2), t2 = __shfl_sync(0xffffffffu, t, 4);
+        const unsigned long long ovf = __shfl_sync(0xffffffffu, w, 6);
+        if (lane == 0) {
+            if (ovf) sh.fallback = 1;
+            else update(0, t, t1, t2);
+#ifdef JF_FX_CHECK
+            sh.dbg[0] = t; sh.dbg[1] = t1; sh.dbg[2] = t2;
+#endif
+        }
+    }
+    __syncthreads();
+    if (sh.fallback) fused_collect<3, KMAX>(a, sh, part, update);  // some partial did not fit: the slot tables have it
+#ifdef JF_FX_CHECK
+    else {  // debug build: the fixed-point totals against the slot-table sums of the same partials
+        fused_collect<3, KMAX>(a, sh, part, [&](int, double s0, double s1, double s2) {
+            const double r0 = fabs(sh.dbg[0] - s0) / fabs(s0), r1 = fabs(sh.dbg[1] - s1) / fabs(s1), r2 = fabs(sh.dbg[2] - s2) / fabs(s2);
+            sh.dbg_max = fmax(sh.dbg_max, fmax(r0, fmax(r1, r2)));
+            sh.dbg_n++;
+        });
+    }
+#endif
 }
 
 __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
@@ -381,8 +466,8 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                         lo = __double2ll_rd(rem * pow2(FX_LO_SHIFT - E));
                         lo = min(max(lo, 0ll), (1ll << FX_BITS) - 1);
                     }
-                    sh.word[2 * q] = (1ull << 56) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
-                    sh.word[2 * q + 1] = (1ull << 56) + (unsigned long long)lo;
+                    sh.word[2 * q] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
+                    sh.word[2 * q + 1] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)lo;
                     sh.overflow[q] = !ok;
                 }
             }
@@ -400,7 +485,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 do {
                     // words 4, 5 and the overflow word share a sector: a poll that sees them complete sees every mark
                     if (lane < 7) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(acc + lane) : "memory");
-                    complete = lane >= 6 || (unsigned)(w >> 56) == gridDim.x;
+                    complete = lane >= 6 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
                 } while (!__all_sync(0xffffffffu, complete));
                 sh.fallback = 0;
             }
@@ -410,7 +495,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 if (blockIdx.x == 0 && lane < 7) a.acc[((xe + 2u) % 3u) * 8 + lane] = 0ull;  // recycle the buffer of the epoch before
                 double d = 0.0;
                 if (lane < 6) {
-                    const unsigned long long body = w & ((1ull << 56) - 1);
+                    const unsigned long long body = w & ((1ull << FX_COUNT_SHIFT) - 1);
                     const int E = sh.expo[(lane >> 1) == 2 ? 1 : 0];
                     if (lane & 1) d = (double)body * pow2(E - FX_LO_SHIFT);
                     else d = (double)((long long)body - (long long)gridDim.x * (1ll << (FX_BITS - 1))) * pow2(E - FX_HI_SHIFT);
@@ -514,6 +599,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
         sh.beta[threadIdx.x] = 0.0;
         sh.lastcur[threadIdx.x] = 1;
     }
+    if (threadIdx.x == 0) sh.scale_ok = sh.fallback = 0;
     for (int i = threadIdx.x; i < 3 * F_MAX_SYS * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
     __syncthreads();
 
@@ -545,6 +631,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
     });
 
     unsigned light_target = 0;
+    unsigned xe = 0;
     int cur = 0;
     for (long long it = 1; it <= a.maxiter; it++) {
         int all = 1;
@@ -644,8 +731,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
                 sh.warp[2][s][warp] = a2;
             }
         }
-        const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
-        fused_collect<3, 10>(a, sh, part, [&](int ss, double pAp, double rAp, double ApAp) {
+        auto update = [&](int ss, double pAp, double rAp, double ApAp) {
             if (sh.done[ss]) return;
             const double rho = sh.rho[ss];
             const double alpha = rho / pAp;
@@ -659,7 +745,20 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
                 sh.beta[ss] = rsnew / rho;
                 sh.rho[ss] = rsnew;
             }
-        });
+            if (a.n_sys == 1) {  // units of the next iteration's fixed-point sums
+                int e0 = 0, e2 = 0;
+                const bool ok = fx_exponent_ok(pAp, &e0) & fx_exponent_ok(ApAp, &e2);
+                sh.expo[0] = e0;
+                sh.expo[1] = e2;
+                sh.scale_ok = ok;
+            }
+        };
+        if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {
+            fused_fx_allreduce<10>(a, sh, epoch, xe, update, [] {});
+        } else {
+            const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+            fused_collect<3, 10>(a, sh, part, update);
+        }
         cur ^= 1;
     }
 
@@ -737,6 +836,8 @@ int jf_cg_fused_stream_configure(jf_ctx *c) {
 
 int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
     a.light_barrier = getenv("JF_CG_CGSYNC") == nullptr;
+    a.exact_sums = a.light_barrier && getenv("JF_CG_SLOT_SUMS") == nullptr;
+    a.acc = (unsigned long long *)((char *)c->d_sync + 64);
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;
