@@ -44,6 +44,7 @@ struct CgArgs {
     double step;
     int apply_update;
     unsigned long long *acc = nullptr;  // single-reduction kernel: 3 x 8 fixed-point accumulators (zeroed before every launch)
+    int fx_test = 0;            // JF_FX_TEST_OVERFLOW=n: CTA 0 declares every n-th fixed-point reduction unrepresentable (tests)
     int exact_sums = 1;         // sums through integer atomics that double as the barrier (JF_CG_SLOT_SUMS=1: slot tables)
     int light_barrier = 1;      // single-reduction kernel: counter barrier without the L1 invalidation (JF_CG_CGSYNC=1: grid.sync)
     int prefetch = 1;           // single-reduction kernel: request the halo Ap right after the barrier (JF_CG_NO_PREFETCH=1: off)

@@ -155,22 +155,28 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
 // The fixed-point all-reduce as a function (streaming kernel; the register-resident kernel has the same statements
 // inline).  `after_barrier` runs in every thread once all CTAs have arrived, before the scalars are formed.
 template <int KMAX, typename U, typename P>
-__device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared &sh, unsigned &epoch, unsigned &xe, U update, P after_barrier) {
+__device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, unsigned &xe,
+                                                   unsigned &light_target, U update, P after_barrier) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     epoch++;
     xe++;
     const int nwarps = blockDim.x >> 5;
+#ifdef JF_FX_CHECK
     const size_t table = (size_t)3 * gridDim.x;
     double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
+#endif
     unsigned long long *acc = a.acc + (xe % 3u) * 8;
     __syncthreads();
     for (int q = warp; q < 3; q += nwarps) {  // (a CTA of a small mesh may have two warps only)
         double x = lane < nwarps ? sh.warp[q][0][lane] : 0.0;
         x = warp_sum(x);
-        if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;  // for the fallback
+#ifdef JF_FX_CHECK
+        if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;
+#endif
         if (lane == 0) {
             const int E = sh.expo[q == 2 ? 1 : 0];
-            const bool ok = fabs(x) < pow2(E + FX_HEADROOM);  // false for NaN
+            const bool ok = fabs(x) < pow2(E + FX_HEADROOM) &&  // false for NaN
+                                    !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0);
             long long hi = 0, lo = 0;
             if (ok) {
                 hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
@@ -224,7 +230,10 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
         }
     }
     __syncthreads();
-    if (sh.fallback) fused_collect<3, KMAX>(a, sh, part, update);  // some partial did not fit: the slot tables have it
+    if (sh.fallback) {  // some partial did not fit: this iteration goes through the slot tables (per-warp partials are still in sh.warp)
+        const double *slots = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+        fused_collect<3, KMAX>(a, sh, slots, update);
+    }
 #ifdef JF_FX_CHECK
     else {  // debug build: the fixed-point totals against the slot-table sums of the same partials
         fused_collect<3, KMAX>(a, sh, part, [&](int, double s0, double s1, double s2) {
@@ -448,17 +457,22 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             epoch++;
             xe++;
             const int nwarps = blockDim.x >> 5;
+#ifdef JF_FX_CHECK
             const size_t table = (size_t)3 * gridDim.x;
             double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
+#endif
             unsigned long long *acc = a.acc + (xe % 3u) * 8;
             __syncthreads();
             for (int q = warp; q < 3; q += nwarps) {  // (a CTA of a small mesh may have two warps only)
                 double x = lane < nwarps ? sh.warp[q][0][lane] : 0.0;
                 x = warp_sum(x);
-                if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;  // for the fallback
+        #ifdef JF_FX_CHECK
+                if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;
+#endif
                 if (lane == 0) {
                     const int E = sh.expo[q == 2 ? 1 : 0];
-                    const bool ok = fabs(x) < pow2(E + FX_HEADROOM);  // false for NaN
+                    const bool ok = fabs(x) < pow2(E + FX_HEADROOM) &&  // false for NaN
+                                    !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0);
                     long long hi = 0, lo = 0;
                     if (ok) {
                         hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
@@ -512,7 +526,10 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 }
             }
             __syncthreads();
-            if (sh.fallback) fused_collect<3, 5>(a, sh, part, update);  // some partial did not fit: the slot tables have it
+            if (sh.fallback) {  // some partial did not fit: this iteration goes through the slot tables (per-warp partials are still in sh.warp)
+                const double *slots = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+                fused_collect<3, 5>(a, sh, slots, update);
+            }
 #ifdef JF_FX_CHECK
             else {  // debug build: the fixed-point totals against the slot-table sums of the same partials
                 fused_collect<3, 5>(a, sh, part, [&](int, double s0, double s1, double s2) {
@@ -754,7 +771,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
             }
         };
         if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {
-            fused_fx_allreduce<10>(a, sh, epoch, xe, update, [] {});
+            fused_fx_allreduce<10>(a, grid, sh, epoch, xe, light_target, update, [] {});
         } else {
             const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
             fused_collect<3, 10>(a, sh, part, update);
@@ -837,6 +854,7 @@ int jf_cg_fused_stream_configure(jf_ctx *c) {
 int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
     a.light_barrier = getenv("JF_CG_CGSYNC") == nullptr;
     a.exact_sums = a.light_barrier && getenv("JF_CG_SLOT_SUMS") == nullptr;
+    a.fx_test = getenv("JF_FX_TEST_OVERFLOW") ? atoi(getenv("JF_FX_TEST_OVERFLOW")) : 0;
     a.acc = (unsigned long long *)((char *)c->d_sync + 64);
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
@@ -857,6 +875,7 @@ int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
     a.prefetch = !no_prefetch;
     a.light_barrier = !cg_sync;
     a.exact_sums = !slot_sums && !cg_sync;
+    a.fx_test = getenv("JF_FX_TEST_OVERFLOW") ? atoi(getenv("JF_FX_TEST_OVERFLOW")) : 0;
     a.acc = (unsigned long long *)((char *)c->d_sync + 64);
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;

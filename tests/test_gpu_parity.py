@@ -265,6 +265,33 @@ def test_resident_and_streaming_cg_agree(beams, monkeypatch):
         assert np.linalg.norm(other[0] - res[4][0]) / np.linalg.norm(res[4][0]) < 5e-5
 
 
+@pytest.mark.parametrize("streamed", [False, True])
+def test_fixed_point_reduction_falls_back_when_a_partial_does_not_fit(beams, monkeypatch, streamed):
+    """JF_FX_TEST_OVERFLOW=3 makes CTA 0 declare every third fixed-point reduction unrepresentable: all CTAs see the
+    mark in the accumulator sector and redo that iteration's sums through the slot tables.  Same trajectory as the
+    pure slot-table run up to the noise floor, and no deadlock."""
+    from jointforces_b200 import _lib
+    c = make_case(0.3, 100.0)
+    res = {}
+    for name, env in (("fixed", {}), ("mixed", {"JF_FX_TEST_OVERFLOW": "3"}), ("slots", {"JF_CG_SLOT_SUMS": "1"})):
+        for k in ("JF_FX_TEST_OVERFLOW", "JF_CG_SLOT_SUMS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams, flags=_lib.JF_FLAG_NO_RESIDENT if streamed else 0) as ctx:
+            assert ctx.info()["cg_fused"] == (2 if streamed else 1)
+            ctx.set_material(*COLLAGEN12)
+            ctx.set_targets(c["f_target"])
+            ctx.set_displacements(np.zeros_like(c["coords"]))
+            relrec, cgit, n = ctx.relax(0.0033, 600, 0.01)
+            res[name] = (ctx.displacements(), cgit[0].copy(), int(n[0]))
+    assert res["fixed"][2] == res["mixed"][2] == res["slots"][2]
+    for other in ("mixed", "slots"):
+        assert np.abs(res[other][1].astype(int) - res["fixed"][1]).max() <= 0.10 * res["fixed"][1].max()   # CG stop is rounding-sensitive
+        assert np.linalg.norm(res[other][0] - res["fixed"][0]) / np.linalg.norm(res["fixed"][0]) < 5e-5
+    assert not np.array_equal(res["mixed"][0], res["fixed"][0])          # the mark really changed the path taken
+
+
 def test_device_and_host_structure_build_agree(beams, monkeypatch):
     """Adjacency, ordering scores, shape tensors and gather lists are built on the device; JF_HOST_SETUP=1 keeps the
     adjacency and the scores on the host.  Same structure -> same arithmetic -> identical bits."""
