@@ -152,8 +152,8 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
     fused_collect<NQ, KMAX>(a, sh, part, update);
 }
 
-// The fixed-point all-reduce as a function (streaming kernel; the register-resident kernel has the same statements
-// inline).  `after_barrier` runs in every thread once all CTAs have arrived, before the scalars are formed.
+// The fixed-point all-reduce of one iteration.  `after_barrier` runs in every thread once all CTAs have arrived, before
+// the scalars are formed (the register-resident kernel requests its halo Ap there).
 template <int KMAX, typename U, typename P>
 __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, unsigned &xe,
                                                    unsigned &light_target, U update, P after_barrier) {
@@ -454,91 +454,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             }
         };
         if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {  // the same decision in every CTA: scale_ok comes from shared totals
-            epoch++;
-            xe++;
-            const int nwarps = blockDim.x >> 5;
-#ifdef JF_FX_CHECK
-            const size_t table = (size_t)3 * gridDim.x;
-            double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
-#endif
-            unsigned long long *acc = a.acc + (xe % 3u) * 8;
-            __syncthreads();
-            for (int q = warp; q < 3; q += nwarps) {  // (a CTA of a small mesh may have two warps only)
-                double x = lane < nwarps ? sh.warp[q][0][lane] : 0.0;
-                x = warp_sum(x);
-        #ifdef JF_FX_CHECK
-                if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;
-#endif
-                if (lane == 0) {
-                    const int E = sh.expo[q == 2 ? 1 : 0];
-                    const bool ok = fabs(x) < pow2(E + FX_HEADROOM) &&  // false for NaN
-                                    !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0);
-                    long long hi = 0, lo = 0;
-                    if (ok) {
-                        hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
-                        const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi), exact
-                        lo = __double2ll_rd(rem * pow2(FX_LO_SHIFT - E));
-                        lo = min(max(lo, 0ll), (1ll << FX_BITS) - 1);
-                    }
-                    sh.word[2 * q] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
-                    sh.word[2 * q + 1] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)lo;
-                    sh.overflow[q] = !ok;
-                }
-            }
-            __syncthreads();
-            unsigned long long w = 0;  // warp 0, lanes 0..6: the accumulator words (6: partials that did not fit)
-            if (warp == 0) {
-                if (lane == 0) {
-                    if (sh.overflow[0] | sh.overflow[1] | sh.overflow[2])
-                        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + 6), "l"(1ull) : "memory");
-                    __threadfence();  // this CTA's Ap rows, fallback partials and the overflow mark are in L2 before it arrives
-                }
-                __syncwarp();
-                if (lane < 6) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(sh.word[lane]) : "memory");
-                bool complete;
-                do {
-                    // words 4, 5 and the overflow word share a sector: a poll that sees them complete sees every mark
-                    if (lane < 7) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(acc + lane) : "memory");
-                    complete = lane >= 6 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
-                } while (!__all_sync(0xffffffffu, complete));
-                sh.fallback = 0;
-            }
-            __syncthreads();  // the barrier proper: every CTA's words are in
-            prefetch_halo();
-            if (warp == 0) {
-                if (blockIdx.x == 0 && lane < 7) a.acc[((xe + 2u) % 3u) * 8 + lane] = 0ull;  // recycle the buffer of the epoch before
-                double d = 0.0;
-                if (lane < 6) {
-                    const unsigned long long body = w & ((1ull << FX_COUNT_SHIFT) - 1);
-                    const int E = sh.expo[(lane >> 1) == 2 ? 1 : 0];
-                    if (lane & 1) d = (double)body * pow2(E - FX_LO_SHIFT);
-                    else d = (double)((long long)body - (long long)gridDim.x * (1ll << (FX_BITS - 1))) * pow2(E - FX_HI_SHIFT);
-                }
-                const double t = d + __shfl_down_sync(0xffffffffu, d, 1);  // lanes 0, 2, 4: high + low part
-                const double t1 = __shfl_sync(0xffffffffu, t, 2), t2 = __shfl_sync(0xffffffffu, t, 4);
-                const unsigned long long ovf = __shfl_sync(0xffffffffu, w, 6);
-                if (lane == 0) {
-                    if (ovf) sh.fallback = 1;
-                    else update(0, t, t1, t2);
-#ifdef JF_FX_CHECK
-                    sh.dbg[0] = t; sh.dbg[1] = t1; sh.dbg[2] = t2;
-#endif
-                }
-            }
-            __syncthreads();
-            if (sh.fallback) {  // some partial did not fit: this iteration goes through the slot tables (per-warp partials are still in sh.warp)
-                const double *slots = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
-                fused_collect<3, 5>(a, sh, slots, update);
-            }
-#ifdef JF_FX_CHECK
-            else {  // debug build: the fixed-point totals against the slot-table sums of the same partials
-                fused_collect<3, 5>(a, sh, part, [&](int, double s0, double s1, double s2) {
-                    const double r0 = fabs(sh.dbg[0] - s0) / fabs(s0), r1 = fabs(sh.dbg[1] - s1) / fabs(s1), r2 = fabs(sh.dbg[2] - s2) / fabs(s2);
-                    sh.dbg_max = fmax(sh.dbg_max, fmax(r0, fmax(r1, r2)));
-                    sh.dbg_n++;
-                });
-            }
-#endif
+            fused_fx_allreduce<5>(a, grid, sh, epoch, xe, light_target, update, prefetch_halo);
         } else {
             const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
             prefetch_halo();
