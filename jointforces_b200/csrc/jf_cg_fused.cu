@@ -180,7 +180,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_gro
             long long hi = 0, lo = 0;
             if (ok) {
                 hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
-                const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi), exact
+                const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi]; rounds only for tiny negative x, by < 2^-9 low units
                 lo = __double2ll_rd(rem * pow2(FX_LO_SHIFT - E));
                 lo = min(max(lo, 0ll), (1ll << FX_BITS) - 1);
             }
