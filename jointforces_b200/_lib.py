@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libjf_b200.so")
+# JF_B200_LIB points at an instrumented build of the same library (profiling only)
+LIB_PATH = os.environ.get("JF_B200_LIB") or os.path.join(_HERE, "_lib", "libjf_b200.so")
 
 JF_FLAG_NO_REORDER = 1
 JF_FLAG_NO_FOLD = 2

@@ -68,13 +68,15 @@ __global__ void __launch_bounds__(256) jf_gather_f_kernel(const int32_t *__restr
     }
 }
 
-// fixed-order reductions: strain energy, |f - f_t|^2 and |f|^2 over free nodes.  RED_CTAS CTAs per system take
+// fixed-order reductions: strain energy, |f - f_t|^2 and |f|^2 over free nodes.  The energy counts only tetrahedra
+// with at least one free node (free nodes are numbered first: some corner < Nf), as saenopy's `_update_energy` does
+// (oracle/saeno_oracle.py `energy_rule`); Et itself keeps every tet's energy for jf_get_element_quantities.  RED_CTAS CTAs per system take
 // fixed strided shares and publish partial sums; the CTA that arrives last (self-resetting ticket) adds them in
 // index order -- deterministic whatever the arrival order.
 constexpr int RED_CTAS = 32;
 constexpr int RED_THREADS = 256;
 
-__global__ void __launch_bounds__(RED_THREADS) jf_reduce_kernel(const double *__restrict__ Et, const double *__restrict__ f,
+__global__ void __launch_bounds__(RED_THREADS) jf_reduce_kernel(const int4 *__restrict__ tets, const double *__restrict__ Et, const double *__restrict__ f,
                                                                 const double *__restrict__ b, jf_sys_state *__restrict__ state,
                                                                 double *__restrict__ partial, unsigned *__restrict__ ticket, long long N,
                                                                 long long Nf, long long Nf_pad, long long T) {
@@ -85,7 +87,10 @@ __global__ void __launch_bounds__(RED_THREADS) jf_reduce_kernel(const double *__
     double e = 0.0, r2 = 0.0, f2 = 0.0;
     const double *E = Et + (long long)s * T;
     const long long stride = (long long)RED_CTAS * RED_THREADS, first = (long long)blockIdx.x * RED_THREADS + threadIdx.x;
-    for (long long t = first; t < T; t += stride) e += E[t];
+    for (long long t = first; t < T; t += stride) {
+        const int4 c = tets[t];
+        if (min(min(c.x, c.y), min(c.z, c.w)) < Nf) e += E[t];
+    }
     const double *fs = f + (long long)s * N * 3;
     const double4 *bs = (const double4 *)(b + (long long)s * Nf_pad * 4);
     for (long long n = first; n < Nf; n += stride) {
@@ -187,7 +192,7 @@ int jf_launch_assembly(jf_ctx *c) {
     jf_gather_f_kernel<<<gf, 256, 0, c->stream>>>(c->d_fn_ptr, c->d_fn_src, c->d_fel, c->d_ft, c->d_f, c->d_b, c->d_state, c->N,
                                                   c->Nf, c->Nf_pad, c->T);
     JF_CUDA(cudaGetLastError());
-    jf_reduce_kernel<<<dim3(RED_CTAS, (unsigned)c->n_sys), RED_THREADS, 0, c->stream>>>(c->d_Et, c->d_f, c->d_b, c->d_state, c->d_red_partial,
+    jf_reduce_kernel<<<dim3(RED_CTAS, (unsigned)c->n_sys), RED_THREADS, 0, c->stream>>>((const int4 *)c->d_tets, c->d_Et, c->d_f, c->d_b, c->d_state, c->d_red_partial,
                                                                                       c->d_red_ticket, c->N, c->Nf, c->Nf_pad, c->T);
     JF_CUDA(cudaGetLastError());
     c->stats.kernel_launches += 2;

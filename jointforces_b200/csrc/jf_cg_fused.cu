@@ -30,6 +30,17 @@
 
 namespace {
 
+// -DJF_CG_TIMING: thread 0 of EVERY CTA accumulates clock64 intervals (FMARK) and prints one line at the end
+#ifdef JF_CG_TIMING
+#define FMARK(i) do { if (threadIdx.x == 0) { long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } } while (0)
+#define FT_ARGS , long long *tacc, long long &tlast
+#define FT_PASS , tacc, tlast
+#else
+#define FMARK(i) do { } while (0)
+#define FT_ARGS
+#define FT_PASS
+#endif
+
 constexpr int F_J = 9;          // block columns per lane half
 constexpr int F_HALO_BATCH = 3;  // one round of loads covers 768 halo nodes (config 2: 282-562 per CTA)
 #ifndef F_REPLICAS
@@ -156,7 +167,7 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
 // the scalars are formed (the register-resident kernel requests its halo Ap there).
 template <int KMAX, typename U, typename P>
 __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, unsigned &xe,
-                                                   unsigned &light_target, U update, P after_barrier) {
+                                                   unsigned &light_target, U update, P after_barrier FT_ARGS) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     epoch++;
     xe++;
@@ -190,6 +201,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_gro
         }
     }
     __syncthreads();
+    FMARK(3);
     unsigned long long w = 0;  // warp 0, lanes 0..6: the accumulator words (6: partials that did not fit)
     if (warp == 0) {
         if (lane == 0) {
@@ -198,13 +210,22 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_gro
             __threadfence();  // this CTA's Ap rows, fallback partials and the overflow mark are in L2 before it arrives
         }
         __syncwarp();
+        FMARK(4);
         if (lane < 6) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(sh.word[lane]) : "memory");
         bool complete;
+#ifdef JF_CG_TIMING
+        bool first = true;
+#endif
         do {
             // words 4, 5 and the overflow word share a sector: a poll that sees them complete sees every mark
             if (lane < 7) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(acc + lane) : "memory");
             complete = lane >= 6 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
+#ifdef JF_CG_TIMING
+            if (first) { FMARK(5); first = false; }
+            if (threadIdx.x == 0) tacc[9]++;
+#endif
         } while (!__all_sync(0xffffffffu, complete));
+        FMARK(6);
         sh.fallback = 0;
     }
     __syncthreads();  // the barrier proper: every CTA's words are in
@@ -230,6 +251,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_gro
         }
     }
     __syncthreads();
+    FMARK(7);
     if (sh.fallback) {  // some partial did not fit: this iteration goes through the slot tables (per-warp partials are still in sh.warp)
         const double *slots = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
         fused_collect<3, KMAX>(a, sh, slots, update);
@@ -338,7 +360,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     });
 
 #ifdef JF_CG_TIMING
-    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
     int cur = 0;
     unsigned light_target = 0;  // arrivals expected at the light barrier so far (thread 0)
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
         int all = 1;
         for (int q = 0; q < a.n_sys; q++) all &= sh.done[q];
         if (all) break;
-        TMARK(0);
+        FMARK(0);
         const bool on = !sh.done[s];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         if (on) {
@@ -379,6 +401,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                     }
                 }
             }
+            FMARK(1);
             // ---- own row: the deferred updates of the previous iteration ------------------------------------
             if (have) {
                 x0 = fma(alpha, p0, x0);
@@ -422,7 +445,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             sh.warp[1][s][warp] = a1;
             sh.warp[2][s][warp] = a2;
         }
-        TMARK(1);
+        FMARK(2);
         auto update = [&](int ss, double pAp, double rAp, double ApAp) {
             if (sh.done[ss]) return;
             const double rho = sh.rho[ss];
@@ -454,19 +477,24 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             }
         };
         if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {  // the same decision in every CTA: scale_ok comes from shared totals
-            fused_fx_allreduce<5>(a, grid, sh, epoch, xe, light_target, update, prefetch_halo);
+            fused_fx_allreduce<5>(a, grid, sh, epoch, xe, light_target, update, prefetch_halo FT_PASS);
         } else {
             const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
             prefetch_halo();
             fused_collect<3, 5>(a, sh, part, update);
+            FMARK(8);
         }
-        TMARK(2);
         cur ^= 1;
     }
 #ifdef JF_CG_TIMING
-    if (threadIdx.x == 0 && blockIdx.x == 0)
-        printf("cg-fused iters %d cycles/iter: top %.0f phaseA %.0f allreduce %.0f  (nh %d)\n", sh.iters[0], (double)tacc[0] / sh.iters[0],
-               (double)tacc[1] / sh.iters[0], (double)tacc[2] / sh.iters[0], nh);
+    if (threadIdx.x == 0) {
+        const double n = sh.iters[0] > 0 ? sh.iters[0] : 1;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("cgt cta %3d sm %3u nh %3d iters %4d | top %5.0f halo %5.0f spmv %5.0f | prep %5.0f fence %5.0f red+poll1 %5.0f pollwait %5.0f post %5.0f slot %5.0f | polls %.2f\n",
+               blockIdx.x, smid, nh, sh.iters[0], tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n,
+               tacc[7] / n, tacc[8] / n, tacc[9] / n);
+    }
 #endif
 
 #ifdef JF_FX_CHECK
@@ -687,7 +715,10 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
             }
         };
         if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {
-            fused_fx_allreduce<10>(a, grid, sh, epoch, xe, light_target, update, [] {});
+#ifdef JF_CG_TIMING
+            long long tacc[10], tlast = 0;
+#endif
+            fused_fx_allreduce<10>(a, grid, sh, epoch, xe, light_target, update, [] {} FT_PASS);
         } else {
             const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
             fused_collect<3, 10>(a, sh, part, update);

@@ -37,7 +37,7 @@ def lib():
         L.so_element_eval.argtypes = [C.c_int, _ip, _dp, _dp, _dp, C.c_int, _dp] + [C.c_double] * 4 + [_dp, _dp, _dp]
         L.so_element_eval.restype = None
         L.so_relax.argtypes = [C.c_int, C.c_int, _dp, _ip, _bp, _dp, _dp, C.c_int, _dp] + [C.c_double] * 4 + \
-                              [C.c_double, C.c_int, C.c_double, _dp, _ip, _dp, _dp, C.c_int]
+                              [C.c_double, C.c_int, C.c_double, _dp, _ip, _dp, _dp, C.c_int, C.c_double]
         L.so_relax.restype = C.c_int
         L.so_pattern_nnz.argtypes = [C.c_int, C.c_int, _ip, _bp]
         L.so_pattern_nnz.restype = C.c_int64
@@ -90,7 +90,7 @@ def assemble(nodes, tets, movable, U, beams, material):
     return e, forces, ssp.csr_matrix((val, col, rowptr), shape=(3 * N, 3 * N))
 
 
-def relax(nodes, tets, movable, f_target, U0, beams, material, step, max_iter, conv_crit, nthreads=0):
+def relax(nodes, tets, movable, f_target, U0, beams, material, step, max_iter, conv_crit, nthreads=0, cg_tol=0.0):
     """Run the whole relaxation.  Returns dict(U, forces, relrec (n+1,3), cg_iters (n,), n_iter,
     t_element, t_cg)."""
     nodes, tets, beams = _c(nodes, np.float64), _c(tets, np.int32), _c(beams, np.float64)
@@ -103,6 +103,6 @@ def relax(nodes, tets, movable, f_target, U0, beams, material, step, max_iter, c
     forces = np.empty((N, 3))
     timing = np.zeros(2)
     n = lib().so_relax(N, T, nodes, tets, mov, ft, U, len(beams), beams, *map(float, material), float(step),
-                       int(max_iter), float(conv_crit), relrec, cgit, forces, timing, int(nthreads))
+                       int(max_iter), float(conv_crit), relrec, cgit, forces, timing, int(nthreads), float(cg_tol))
     return dict(U=U, forces=forces, relrec=relrec[: n + 1].copy(), cg_iters=cgit[:n].copy(), n_iter=n,
                 t_element=timing[0], t_cg=timing[1])

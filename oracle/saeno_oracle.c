@@ -157,6 +157,7 @@ typedef struct {
     int64_t *rowptr; /* 3N+1 */
     int32_t *col;    /* nnz   */
     int64_t *slot;   /* T*144 : CSR position of K_el entry, or -1 (row of a fixed node) */
+    uint8_t *count_energy; /* T : 1 if the tet has at least one free node (its energy counts, see update_f_and_K) */
 } so_pattern;
 
 static int cmp_i32(const void *a, const void *b) {
@@ -205,6 +206,9 @@ static so_pattern *pattern_build(int N, int T, const int32_t *tets, const uint8_
         }
     }
     p->slot = (int64_t *)malloc(sizeof(int64_t) * 144 * (size_t)T);
+    p->count_energy = (uint8_t *)malloc((size_t)T);
+    for (int t = 0; t < T; t++)
+        p->count_energy[t] = movable[tets[4 * t]] | movable[tets[4 * t + 1]] | movable[tets[4 * t + 2]] | movable[tets[4 * t + 3]];
     for (int t = 0; t < T; t++)
         for (int m = 0; m < 4; m++) {
             int32_t rn = tets[4 * t + m];
@@ -233,6 +237,7 @@ static void pattern_free(so_pattern *p) {
     free(p->rowptr);
     free(p->col);
     free(p->slot);
+    free(p->count_energy);
     free(p);
 }
 
@@ -282,7 +287,11 @@ static int cg_solve(const so_pattern *p, const double *val, const double *b, dou
     return it > maxiter ? maxiter : it;
 }
 
-/* evaluate + assemble: forces (N,3), CSR values, strain energy */
+/* evaluate + assemble: forces (N,3), CSR values, strain energy.
+ * The global energy counts only tetrahedra with at least one free node (saenopy `_update_energy`, as SAENO's
+ * `countEnergy`: a tet whose four nodes all carry a displacement condition cannot change and is left out of
+ * E_glo).  With the reference's boundary conditions (outer shell held at zero, simulation.py:127-129) such tets
+ * have zero energy anyway; the rule matters for non-zero prescribed displacements. */
 static double update_f_and_K(const so_pattern *p, const int32_t *tets, const double *U, const double *Phi,
                              const double *V, int Nb, const double *s, const so_material *m, double *E, double *f_el,
                              double *K_el, double *forces, double *val) {
@@ -292,7 +301,7 @@ static double update_f_and_K(const so_pattern *p, const int32_t *tets, const dou
     memset(val, 0, sizeof(double) * (size_t)p->nnz);
     double e = 0.0;
     for (int t = 0; t < T; t++) {
-        e += E[t];
+        if (p->count_energy[t]) e += E[t];
         for (int mm = 0; mm < 4; mm++)
             for (int i = 0; i < 3; i++) forces[3 * tets[4 * t + mm] + i] += f_el[12 * (size_t)t + 3 * mm + i];
         const int64_t *sl = p->slot + 144 * (size_t)t;
@@ -308,7 +317,9 @@ static double update_f_and_K(const so_pattern *p, const int32_t *tets, const dou
 int so_relax(int N, int T, const double *nodes, const int32_t *tets, const uint8_t *movable, const double *f_target,
              double *U, int Nb, const double *beams, double k, double d0, double ls, double ds, double step,
              int max_iter, double conv_crit, double *relrec, int32_t *cg_iters, double *forces_out,
-             double *timing /* [0]=element+assembly s, [1]=cg s, may be NULL */, int nthreads) {
+             double *timing /* [0]=element+assembly s, [1]=cg s, may be NULL */, int nthreads,
+             double cg_tol /* <= 0: saenopy's 1e-5 (on squared norms) */) {
+    if (!(cg_tol > 0)) cg_tol = 0.00001;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -349,7 +360,7 @@ int so_relax(int N, int T, const double *nodes, const int32_t *tets, const uint8
         for (int i = 0; i < N; i++)
             for (int c = 0; c < 3; c++) ff[3 * i + c] = movable[i] ? forces[3 * i + c] - f_target[3 * i + c] : 0.0;
         t0 = NOW();
-        cg_iters[it] = cg_solve(p, val, ff, uu, 3 * N, 0.00001, w1, w2, w3);
+        cg_iters[it] = cg_solve(p, val, ff, uu, 3 * N, cg_tol, w1, w2, w3);
         t_cg += NOW() - t0;
         double du = 0.0;
         for (int i = 0; i < N; i++)

@@ -102,10 +102,13 @@ class SemiAffineFiberMaterial:
 
     ``mode='closed'`` evaluates the integrals in closed form (expm1-safe).  ``mode='lut'``
     emulates saenopy's sampled table (lambda = -1 ... 4, step 1e-6, w'' clipped at 1e11, w' and w
-    by cumulative sums re-zeroed at lambda=0; index rule selectable because it is not known).
+    by cumulative sums re-zeroed at lambda=0).  The lookup rule is recalled, not verified (saenopy is absent):
+    ``lut_index='interp'`` (default) is linear interpolation between the samples floor(q) and floor(q)+1 with the
+    index clamped two short of the end -- saenopy's ``sample_and_integrate_function.lookup`` as recalled
+    [RECALL]; 'ceil' / 'round' / 'floor' read a single sample and are kept to bound the effect of the rule.
     """
 
-    def __init__(self, k, d0=None, lambda_s=None, ds=None, mode="closed", lut_index="ceil"):
+    def __init__(self, k, d0=None, lambda_s=None, ds=None, mode="closed", lut_index="interp"):
         self.k = float(k)
         self.d0 = float(d0) if d0 is not None else 1e30
         self.lambda_s = float(lambda_s) if lambda_s is not None else 1e30
@@ -170,6 +173,15 @@ class SemiAffineFiberMaterial:
         if self._lut is None:
             self._build_lut()
         q = (np.asarray(lam, dtype=np.float64) - self._LMIN) / self._LSTEP
+        if self.lut_index == "interp":
+            li = np.floor(q)
+            dli = q - li
+            last = (self._LMAX - self._LMIN) / self._LSTEP - 2
+            at_end = li > last
+            li = np.where(at_end, float(int(last)), li)
+            dli = np.where(at_end, 0.0, dli)
+            lii = np.clip(li.astype(np.int64), 0, len(self._lut[0]) - 2)
+            return tuple((1 - dli) * tab[lii] + dli * tab[lii + 1] for tab in self._lut)
         if self.lut_index == "ceil":
             idx = np.ceil(q)
         elif self.lut_index == "round":
@@ -247,6 +259,7 @@ class Solver:
         self.K_glo = None
         self.relrec = None
         self.cg_iterations = []      # CG iterations taken in each Newton step (diagnostic)
+        self.energy_rule = "free_tets"   # E_glo counts tets with >= 1 free node (saenopy [RECALL]); "all" = every tet
         self.set_beams(300)
 
     # --- setup --------------------------------------------------------------------------------
@@ -323,6 +336,7 @@ class Solver:
         filt = np.broadcast_to(free_row[:, :, None, None, None], (nt, 4, 4, 3, 3))
         rows = np.broadcast_to((3 * T)[:, :, None, None, None] + np.arange(3)[None, None, None, :, None], (nt, 4, 4, 3, 3))
         cols = np.broadcast_to((3 * T)[:, None, :, None, None] + np.arange(3)[None, None, None, None, :], (nt, 4, 4, 3, 3))
+        self._count_energy = np.any(free_row, axis=1)              # (T,) tets whose energy counts in E_glo
         self._K_filter = filt.ravel().copy()
         self._K_rows = rows.ravel()[self._K_filter]
         self._K_cols = cols.ravel()[self._K_filter]
@@ -367,7 +381,9 @@ class Solver:
             t = slice(i * self.BATCH, (i + 1) * self.BATCH)
             e, f_el[t], K_el[t] = self.element_quantities(t)
             m.cell_energy[t] = e
-            m.strain_energy += np.sum(e)
+            # only tetrahedra with at least one free node count (saenopy `_update_energy` / SAENO `countEnergy`
+            # [RECALL]); all-fixed tets cannot change.  Zero anyway under simulation.py:127-129 (outer shell at 0).
+            m.strain_energy += np.sum(e[self._count_energy[t]]) if self.energy_rule == "free_tets" else np.sum(e)
         n = len(m.nodes)
         m.forces = ssp.coo_matrix((f_el.ravel(), (self._f_rows, self._f_cols)), shape=(n, 3)).toarray()
         self.K_glo = ssp.coo_matrix((K_el.ravel()[self._K_filter], (self._K_rows, self._K_cols)),

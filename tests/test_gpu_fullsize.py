@@ -92,3 +92,70 @@ def test_fullsize_relaxation_scales_with_load_for_linear_material(big_case, beam
     assert np.abs(cgit[0].astype(int) - cgit[1]).max() <= 0.03 * cgit[0].max()    # CG stop is rounding-sensitive
     assert np.linalg.norm(U1 - 2.5 * U0) < 1e-3 * np.linalg.norm(U1)
     assert np.allclose(relrec[1][:, 1], 6.25 * relrec[0][:, 1], rtol=1e-3)
+
+
+# ---- committed oracle fixtures at the BASELINE sizes (tests/golden/make_oracle_fullsize.py) -----------------------
+import os
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# name -> (kernel the default path must take: (cg_resident, cg_fused), tolerance on the CG iteration total)
+FULL_CASES = {
+    "cfg2_full": ((2, 1), 0.02),   # register-resident single-reduction kernel (the bench headline)
+    "cfg3_rowA": ((2, 1), 0.02),
+    "cfg3_rowB": ((2, 1), 0.02),
+    "cfg4_full": ((0, 2), 0.02),   # streaming single-reduction kernel
+    "cfg5_loose": ((0, 0), 0.02),  # plain HBM-bound streaming kernel (roofline_large of bench.py)
+    "cfg5_tight": ((0, 0), 0.02),
+}
+
+
+def _full_case(g):
+    from jointforces_b200.mesh import generate_spherical_inclusion
+    from jointforces_b200.simulation import spherical_boundary_conditions
+    coords, tets = generate_spherical_inclusion(length_factor=float(g["length_factor"]))
+    assert len(coords) == int(g["n_nodes"]) and len(tets) == int(g["n_tets"])
+    bc = spherical_boundary_conditions(coords, 100e-6, 10000e-6, float(g["pressure"]))
+    movable = np.any(np.isnan(bc["displacement"]), axis=1)
+    return coords, tets.astype(np.int32), movable, np.nan_to_num(bc["forces"])
+
+
+@pytest.mark.parametrize("name", list(FULL_CASES))
+def test_fullsize_relaxation_matches_oracle_fixture(name, beams, capsys):
+    """The CUDA path against the committed CPU-oracle solution on the mesh the benchmark numbers are quoted on:
+    Newton iterations equal, displacements within 1e-4 relative L2 (on the stored node subset), lookup-table curve
+    within 1e-3 (BASELINE tolerances); the signed mean CG-iteration difference per Newton step is reported."""
+    from jointforces_b200 import _lib
+    from jointforces_b200.simulation import radial_median_curve, lookup_bins
+    path = os.path.join(GOLDEN, "oracle_full_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("fixture missing")
+    g = np.load(path)
+    kernel, cg_tol_total = FULL_CASES[name]
+    coords, tets, movable, ft = _full_case(g)
+    with _lib.Context(coords, tets, movable, beams=beams) as ctx:
+        info = ctx.info()
+        ctx.set_material(*g["material"])
+        ctx.set_targets(ft)
+        ctx.set_displacements(np.zeros_like(coords))
+        relrec, cgit, n = ctx.relax(float(g["step"]), int(g["max_iter"]), 0.01, cg_tol=float(g["cg_tol"]))
+        U = ctx.displacements()
+    fused = info["cg_fused"] if float(g["cg_tol"]) == 0.0 else 0   # tight tolerances take the classic two-reduction kernels
+    assert (info["cg_resident"], info["cg_fused"]) == kernel, info
+    assert int(n[0]) == len(g["relrec"]) - 1
+    stride = int(g["stride"])
+    err = np.linalg.norm(U[::stride] - g["U_sub"]) / np.linalg.norm(g["U_sub"])
+    d = cgit[0].astype(np.int64) - g["cg_iters"]
+    with capsys.disabled():
+        print("\n[%s] %d nodes, kernel (resident %d, fused %d), %d Newton steps, CG iterations %d vs oracle %d: signed mean "
+              "difference %+.2f per step (max |d| %d), |U-U_oracle|/|U_oracle| = %.2e"
+              % (name, len(coords), info["cg_resident"], fused, n[0], cgit[0].sum(), g["cg_iters"].sum(), d.mean(),
+                 np.abs(d).max(), err))
+    assert err < 1e-4, err
+    assert abs(np.linalg.norm(U) / float(g["U_norm"]) - 1) < 1e-4
+    assert np.allclose(relrec[0][:, 1], g["relrec"][:, 1], rtol=1e-4)
+    assert abs(int(d.sum())) <= cg_tol_total * g["cg_iters"].sum()
+    x, _ = lookup_bins()
+    curve = radial_median_curve(coords, U, 100e-6, x)
+    ok = ~np.isnan(g["curve"])
+    assert np.array_equal(np.isnan(curve), ~ok)
+    assert np.max(np.abs(curve[ok] / g["curve"][ok] - 1)) < 1e-3

@@ -391,7 +391,10 @@ def test_degenerate_problems_do_not_crash(beams):
         ctx.set_displacements(U)
         relrec, cgit, n = ctx.relax(0.1, 3, 0.01)
         assert np.array_equal(ctx.displacements(), U) and np.all(cgit[0] == 0)
-        assert relrec[0][-1, 1] > 0        # strain energy of the prescribed stretch
+        # the prescribed stretch strains tet 1, but E_glo counts only tets with a free node (saenopy `_update_energy`,
+        # oracle `energy_rule`): none here.  The per-tet energies keep it.
+        assert relrec[0][-1, 1] == 0
+        assert ctx.element_quantities(want_K=False)[0][1] > 0
     # node 5 is free but belongs to no tet (empty stiffness row); nodes 1-4 fixed so the problem is well posed
     mov = np.array([1, 0, 0, 0, 0, 1], np.uint8)
     with _lib.Context(nodes, tets, mov, beams=beams) as ctx:
@@ -456,6 +459,10 @@ def test_irregular_random_mesh_matches_oracle(beams):
     assert np.array_equal(U[~movable], U0[~movable])
     assert np.linalg.norm(U - ref["U"]) / np.linalg.norm(ref["U"]) < 1e-4
     assert np.abs(f - ref["forces"]).max() < 1e-3 * np.abs(ref["forces"]).max()
+    # the sheared bottom layer holds tets with four fixed nodes and non-zero strain: E_glo must leave them out
+    # on both sides (saenopy's rule, oracle `energy_rule`), so the logged energies agree from the first row on
+    assert (~np.any(movable[tets], axis=1)).sum() > 0
+    assert np.allclose(relrec[0][:, 1], ref["relrec"][:, 1], rtol=1e-6)
 
 
 def test_hub_node_beyond_the_device_setup_capacity(beams, capfd, monkeypatch):
