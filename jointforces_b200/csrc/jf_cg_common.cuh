@@ -47,7 +47,9 @@ struct CgArgs {
     int fx_test = 0;            // JF_FX_TEST_OVERFLOW=n: CTA 0 declares every n-th fixed-point reduction unrepresentable (tests)
     int exact_sums = 1;         // sums through integer atomics that double as the barrier (JF_CG_SLOT_SUMS=1: slot tables)
     int light_barrier = 1;      // single-reduction kernel: counter barrier without the L1 invalidation (JF_CG_CGSYNC=1: grid.sync)
-    int prefetch = 1;           // single-reduction kernel: request the halo Ap right after the barrier (JF_CG_NO_PREFETCH=1: off)
+    int prefetch = 1;           // single-reduction kernel: request the halo Ap ahead of its use (JF_CG_NO_PREFETCH=1: off)
+    int fenced = 0;             // register-resident single-reduction kernel: fence/acquire ordering of the Ap rows (JF_CG_FENCED=1)
+    int launch_seq = 0;         // CG launches of this context so far: upper half of the Ap rows' epoch tag
 };
 
 // one 32-byte vector entry with a single 256-bit load (LDG.E.256 on sm_100a): a gathered node costs
@@ -64,6 +66,12 @@ __device__ __forceinline__ double4 ld_node_l2(const double4 *p) {
     double4 v;
     asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
+}
+
+// one 32-byte vector entry with a single 256-bit store (STG.E.256): `*p = make_double4(..)` compiles to two 128-bit
+// stores (double4 is 16-byte aligned), which a concurrent reader can see half done
+__device__ __forceinline__ void st_node(double4 *p, double x, double y, double z, double w) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

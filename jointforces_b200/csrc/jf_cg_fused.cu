@@ -30,9 +30,9 @@
 
 namespace {
 
-// -DJF_CG_TIMING: thread 0 of EVERY CTA accumulates clock64 intervals (FMARK) and prints one line at the end
+// -DJF_CG_TIMING: thread 32 (lane 0 of the synchronising warp) of EVERY CTA accumulates clock64 intervals (FMARK) and prints one line at the end
 #ifdef JF_CG_TIMING
-#define FMARK(i) do { if (threadIdx.x == 0) { long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } } while (0)
+#define FMARK(i) do { if (threadIdx.x == 32) { long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } } while (0)
 #define FT_ARGS , long long *tacc, long long &tlast
 #define FT_PASS , tacc, tlast
 #else
@@ -41,8 +41,8 @@ namespace {
 #define FT_PASS
 #endif
 
-constexpr int F_J = 9;          // block columns per lane half
-constexpr int F_HALO_BATCH = 3;  // one round of loads covers 768 halo nodes (config 2: 282-562 per CTA)
+constexpr int F_JR = 8;         // block columns per lane half in registers; a ninth (slices 17-18 blocks wide: few) lives in shared memory
+constexpr int F_HALO_BATCH = 2;  // one round of loads covers 512 foreign halo nodes (config 2: 154-434 per CTA)
 #ifndef F_REPLICAS
 #define F_REPLICAS 4
 #endif
@@ -54,8 +54,7 @@ struct FusedShared {
     int done[F_MAX_SYS], iters[F_MAX_SYS], lastcur[F_MAX_SYS];
     // fixed-point all-reduce (one system): exponents of the previous iteration's p.Ap and Ap.Ap, words to add
     int expo[2], scale_ok, fallback;
-    unsigned long long word[6];
-    int overflow[3];
+    unsigned long long word[8];  // 0..5: two limbs of each sum, 6: overflow mark; each with this CTA's arrival in the top bits
 #ifdef JF_FX_CHECK
     double dbg[3], dbg_max;
     int dbg_n;
@@ -75,12 +74,19 @@ __device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &targ
         __threadfence();  // (red.release.gpu compiles to the same MEMBAR + REDG sequence)
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned seen;
-        do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        do {  // acquire: pairs with the arrivals' fence + red (LDG.STRONG.GPU + CCTL.IVALL; this kernel keeps nothing in L1)
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
         } while (seen < target);
     }
     __syncthreads();
 }
+
+// release fence at gpu scope: MEMBAR.ALL.GPU (__threadfence() is fence.sc: MEMBAR.SC.GPU)
+__device__ __forceinline__ void fence_release_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// named CTA barriers of the fixed-point all-reduce (0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- all-reduce through integer atomics that double as the grid barrier (one system) --------------------------
 // Each of the three sums is accumulated exactly as an 88-bit fixed-point number in two 64-bit words (44 bits each, the
@@ -97,11 +103,13 @@ constexpr int FX_HI_SHIFT = FX_BITS - 2 - FX_HEADROOM, FX_LO_SHIFT = FX_HI_SHIFT
 
 __device__ __forceinline__ double pow2(int k) { return __longlong_as_double((long long)(k + 1023) << 52); }  // -1022 <= k <= 1023
 
+// e = ilogb(v) + 1 for a positive normal v, straight from the exponent field (a handful of integer instructions on the
+// serial path of every iteration); false for zero, negative, subnormal, infinite, NaN or out-of-range values
 __device__ __forceinline__ bool fx_exponent_ok(double v, int *e) {
-    if (!(v > 0.0) || !isfinite(v)) return false;
-    const int k = ilogb(v) + 1;
+    const int hi = __double2hiint(v);
+    const int k = ((hi >> 20) & 0x7ff) - 1022;
     *e = k;
-    return k > -900 + FX_LO_SHIFT && k < 900 - FX_HEADROOM;
+    return hi > 0 && k > -900 + FX_LO_SHIFT && k < 900 - FX_HEADROOM;
 }
 
 // first half: publish the CTA's partial sums and pass the grid barrier
@@ -163,11 +171,93 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
     fused_collect<NQ, KMAX>(a, sh, part, update);
 }
 
-// The fixed-point all-reduce of one iteration.  `after_barrier` runs in every thread once all CTAs have arrived, before
-// the scalars are formed (the register-resident kernel requests its halo Ap there).
+// alpha, the new r.r, the stop decision, beta and the units of the next fixed-point sums from the three totals of an
+// iteration.  ln < 0: one thread does everything (slot-table path); ln >= 0: called by a whole warp with ln = lane, which
+// shares the serial pieces -- lane 0 divides rho / pAp while lane 1 forms 1 / rho and lanes 2, 3 take the exponents; the
+// dependent chain is one division instead of two.  Both forms execute the same operations on the same inputs, so the
+// two paths agree bit for bit (beta = rsnew * (1 / rho) in both).
+__device__ __forceinline__ void fused_update_scalars(FusedShared &sh, int ss, double pAp, double rAp, double ApAp, int ln, long long it,
+                                                     long long maxiter, double tol, bool want_expo, int cur) {
+    if (sh.done[ss]) return;
+    const double rho = sh.rho[ss];
+    double alpha, inv_rho;
+    int e = 0;
+    bool eok = true;
+    if (ln < 0) {
+        alpha = rho / pAp;
+        inv_rho = 1.0 / rho;
+    } else {
+        const double qv = (ln == 1 ? 1.0 : rho) / (ln == 1 ? rho : pAp);
+        if (want_expo && (ln == 2 || ln == 3)) eok = fx_exponent_ok(ln == 3 ? ApAp : pAp, &e);
+        alpha = __shfl_sync(0xffffffffu, qv, 0);
+        inv_rho = __shfl_sync(0xffffffffu, qv, 1);
+    }
+    const double rsnew = fma(alpha * alpha, ApAp, fma(-2.0 * alpha, rAp, rho));  // r'.r' without a second pass
+    if (ln <= 0) {
+        sh.alpha[ss] = alpha;
+        sh.iters[ss] = (int)it;
+        sh.lastcur[ss] = cur;  // streaming kernel: generation that holds this iteration's p
+        if (rsnew < tol * sh.normb[ss] || it == maxiter || !(rsnew > 0.0)) {
+            sh.done[ss] = 1;  // the pending x += alpha p is applied after the loop
+        } else {
+            sh.beta[ss] = rsnew * inv_rho;
+            sh.rho[ss] = rsnew;
+        }
+    }
+    if (!want_expo) return;
+    if (ln < 0) {  // units of the next iteration's fixed-point sums
+        int e0 = 0, e2 = 0;
+        const bool ok = fx_exponent_ok(pAp, &e0) & fx_exponent_ok(ApAp, &e2);
+        sh.expo[0] = e0;
+        sh.expo[1] = e2;
+        sh.scale_ok = ok;
+    } else {
+        const unsigned okm = __ballot_sync(0xffffffffu, eok);
+        if (ln == 2) sh.expo[0] = e;
+        if (ln == 3) sh.expo[1] = e;
+        if (ln == 0) sh.scale_ok = okm == 0xffffffffu;
+    }
+}
+
+// the slot-table all-reduce of one iteration of the loops below, out of line: it runs in the first iteration (no scale
+// yet), when a partial sum does not fit the fixed-point words, and for lockstep batches -- keeping it out of the hot
+// loop's instruction stream
+struct SlotCounters { unsigned epoch, light_target; };
+struct FxPrev { unsigned long long w0 = 0, w1 = 0; };  // per lane: value of its accumulator word when the set's previous use completed
+template <int KMAX>
+__device__ __noinline__ SlotCounters fused_slot_allreduce(CgArgs a, FusedShared *shp, unsigned epoch, unsigned light_target, long long it,
+                                                          bool want_expo, int cur) {
+    // (arguments by value and the counters returned: a reference parameter would pin the caller's copy to local memory)
+    FusedShared &sh = *shp;
+    cg::grid_group grid = cg::this_grid();
+    const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+    fused_collect<3, KMAX>(a, sh, part, [&](int ss, double s0, double s1, double s2) {
+        fused_update_scalars(sh, ss, s0, s1, s2, -1, it, a.maxiter, a.tol, want_expo, cur);
+    });
+    return SlotCounters{epoch, light_target};
+}
+
+// The fixed-point all-reduce of one iteration (one system).  `update(s, pAp, rAp, ApAp, lane)` is called by the first
+// lanes of the synchronising warp together and leaves the scalars in shared memory; `request()` runs once in every
+// thread and issues the loads of what the thread needs from other CTAs in the next iteration.
+//
+// Roles (the critical path of an iteration is this function, so its serial pieces run side by side):
+//   warp 0  "prep"  adds the warps' partial sums and converts them to fixed-point words
+//   warp 1  "sync"  adds the words to the accumulators (integer atomics that carry the arrival count), polls until every
+//                   CTA's are in, decodes the totals and forms alpha, beta, the stop decision and the next exponents
+//   others          wait for the scalars
+// Two orderings of the data other CTAs read afterwards (the Ap rows):
+//   fenced = false  the rows validate themselves (epoch tag in their fourth word, written and read with the row as one
+//                   32-byte access), so nothing orders them against the atomics: no fence, relaxed poll, and
+//                   `request()` runs BEFORE the poll -- the loads travel while the CTAs arrive.
+//   fenced = true   producer: stores -> bar.sync -> fence.gpu -> red (same thread); consumer: ld.acquire poll that reads
+//                   the complete counts -> bar -> `request()`.  The formally ordered path (JF_CG_FENCED=1, and always
+//                   for the streaming kernel, whose rows carry no tag).
+// The overflow mark travels in a seventh word that carries its own arrival count, so "complete" covers it.
 template <int KMAX, typename U, typename P>
-__device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, unsigned &xe,
-                                                   unsigned &light_target, U update, P after_barrier FT_ARGS) {
+__device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared &sh, unsigned &epoch, unsigned &xe, FxPrev &prev,
+                                                   unsigned &light_target, bool fenced, long long it, bool want_expo, int cur, U update,
+                                                   P request FT_ARGS) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     epoch++;
     xe++;
@@ -176,19 +266,29 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_gro
     const size_t table = (size_t)3 * gridDim.x;
     double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
 #endif
-    unsigned long long *acc = a.acc + (xe % 3u) * 8;
-    __syncthreads();
-    for (int q = warp; q < 3; q += nwarps) {  // (a CTA of a small mesh may have two warps only)
-        double x = lane < nwarps ? sh.warp[q][0][lane] : 0.0;
-        x = warp_sum(x);
+    // Two accumulator sets alternate and are never cleared during a launch: the words only grow, and the sum of one use is
+    // the difference to the value the set had when its previous use completed (`prev`, the same in every CTA because a
+    // set is complete -- and stays untouched until everyone has read it -- when a CTA leaves the poll).  Nothing has to
+    // be ordered against a clearing store.
+    unsigned long long *acc = a.acc + (xe & 1u) * 8;
+    __syncthreads();  // the warps' partials are in sh.warp; every Ap store of this CTA has been issued
+    FMARK(3);
+    if (warp == 0) {
+        // lanes 8q .. 8q+7 add the (at most eight) warp partials of sum q: the same shuffle tree as warp_sum over 8 lanes
+        const int q = lane >> 3, wsrc = lane & 7;
+        double x = (q < 3 && wsrc < nwarps) ? sh.warp[q][0][wsrc] : 0.0;
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
 #ifdef JF_FX_CHECK
-        if (lane < F_REPLICAS) part[lane * table + (size_t)q * gridDim.x + blockIdx.x] = x;
+        if (q < 3 && wsrc < F_REPLICAS) part[wsrc * table + (size_t)q * gridDim.x + blockIdx.x] = x;
 #endif
-        if (lane == 0) {
+        bool ok = true;
+        long long hi = 0, lo = 0;
+        if (q < 3 && wsrc == 0) {
             const int E = sh.expo[q == 2 ? 1 : 0];
-            const bool ok = fabs(x) < pow2(E + FX_HEADROOM) &&  // false for NaN
-                                    !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0);
-            long long hi = 0, lo = 0;
+            ok = fabs(x) < pow2(E + FX_HEADROOM) &&  // false for NaN
+                 !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0);
             if (ok) {
                 hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
                 const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi]; rounds only for tiny negative x, by < 2^-9 low units
@@ -197,41 +297,40 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_gro
             }
             sh.word[2 * q] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
             sh.word[2 * q + 1] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)lo;
-            sh.overflow[q] = !ok;
         }
-    }
-    __syncthreads();
-    FMARK(3);
-    unsigned long long w = 0;  // warp 0, lanes 0..6: the accumulator words (6: partials that did not fit)
-    if (warp == 0) {
-        if (lane == 0) {
-            if (sh.overflow[0] | sh.overflow[1] | sh.overflow[2])
-                asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + 6), "l"(1ull) : "memory");
-            __threadfence();  // this CTA's Ap rows, fallback partials and the overflow mark are in L2 before it arrives
-        }
+        const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+        if (lane == 0) sh.word[6] = (1ull << FX_COUNT_SHIFT) + (bad ? 1ull : 0ull);  // the overflow mark arrives like a sum
+        __syncwarp();
+        named_bar_arrive(1, 64);            // words are in shared memory (bar.arrive orders the stores before it)
+        if (fenced) named_bar_sync(2, blockDim.x);  // every CTA has arrived
+        request();
+    } else if (warp == 1) {
+        if (fenced && lane == 0) fence_release_gpu();  // this CTA's rows (and slot partials) are in L2 before its words arrive
         __syncwarp();
         FMARK(4);
-        if (lane < 6) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(sh.word[lane]) : "memory");
+        named_bar_sync(1, 64);
+        FMARK(5);
+        unsigned long long w = 0, raw = 0;  // lanes 0..6: the accumulator words (6: overflow marks), this use's share of them
+        const unsigned long long before = (xe & 1u) ? prev.w1 : prev.w0;
+        if (lane < 7) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(sh.word[lane]) : "memory");
+        if (!fenced) request();
         bool complete;
-#ifdef JF_CG_TIMING
-        bool first = true;
-#endif
         do {
-            // words 4, 5 and the overflow word share a sector: a poll that sees them complete sees every mark
-            if (lane < 7) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(acc + lane) : "memory");
-            complete = lane >= 6 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
+            if (lane < 7) {
+                if (fenced) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane) : "memory");
+                else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane) : "memory");
+            }
+            w = raw - before;
+            complete = lane >= 7 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
 #ifdef JF_CG_TIMING
-            if (first) { FMARK(5); first = false; }
-            if (threadIdx.x == 0) tacc[9]++;
+            if (threadIdx.x == 32) tacc[9]++;
 #endif
         } while (!__all_sync(0xffffffffu, complete));
         FMARK(6);
-        sh.fallback = 0;
-    }
-    __syncthreads();  // the barrier proper: every CTA's words are in
-    after_barrier();
-    if (warp == 0) {
-        if (blockIdx.x == 0 && lane < 7) a.acc[((xe + 2u) % 3u) * 8 + lane] = 0ull;  // recycle the buffer of the epoch before
+        if (fenced) named_bar_arrive(2, blockDim.x);  // the barrier proper: the other warps may read what other CTAs wrote
+        if (xe & 1u) prev.w1 = raw;
+        else prev.w0 = raw;
+        FMARK(10);
         double d = 0.0;
         if (lane < 6) {
             const unsigned long long body = w & ((1ull << FX_COUNT_SHIFT) - 1);
@@ -240,21 +339,26 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, cg::grid_gro
             else d = (double)((long long)body - (long long)gridDim.x * (1ll << (FX_BITS - 1))) * pow2(E - FX_HI_SHIFT);
         }
         const double t = d + __shfl_down_sync(0xffffffffu, d, 1);  // lanes 0, 2, 4: high + low part
-        const double t1 = __shfl_sync(0xffffffffu, t, 2), t2 = __shfl_sync(0xffffffffu, t, 4);
-        const unsigned long long ovf = __shfl_sync(0xffffffffu, w, 6);
-        if (lane == 0) {
-            if (ovf) sh.fallback = 1;
-            else update(0, t, t1, t2);
+        const double t0 = __shfl_sync(0xffffffffu, t, 0), t1 = __shfl_sync(0xffffffffu, t, 2), t2 = __shfl_sync(0xffffffffu, t, 4);
+        const unsigned long long ovf = __shfl_sync(0xffffffffu, w, 6) & ((1ull << FX_COUNT_SHIFT) - 1);
+        if (lane == 0) sh.fallback = ovf ? 1 : 0;
+        FMARK(11);
+        if (!ovf) update(0, t0, t1, t2, lane);  // the whole warp: the lanes share the serial pieces
+        FMARK(8);
+        if (fenced) request();  // after the scalars: loads in flight would hold up the scalar chain
 #ifdef JF_FX_CHECK
-            sh.dbg[0] = t; sh.dbg[1] = t1; sh.dbg[2] = t2;
+        if (lane == 0) { sh.dbg[0] = t0; sh.dbg[1] = t1; sh.dbg[2] = t2; }
 #endif
-        }
+    } else {
+        if (fenced) named_bar_sync(2, blockDim.x);
+        request();
     }
-    __syncthreads();
+    __syncthreads();  // the scalars are in shared memory
     FMARK(7);
     if (sh.fallback) {  // some partial did not fit: this iteration goes through the slot tables (per-warp partials are still in sh.warp)
-        const double *slots = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
-        fused_collect<3, KMAX>(a, sh, slots, update);
+        const SlotCounters sc = fused_slot_allreduce<KMAX>(a, &sh, epoch, light_target, it, want_expo, cur);
+        epoch = sc.epoch;
+        light_target = sc.light_target;
     }
 #ifdef JF_FX_CHECK
     else {  // debug build: the fixed-point totals against the slot-table sums of the same partials
@@ -282,9 +386,16 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     const bool owner = have && half == 0;
     const long long row = sl * 32 + (rloc & 31);
     const long long vstride = a.Nf_pad * 4;
-    double *hr = (double *)dyn_smem;             // hmax * 3: r of every halo node, advanced locally each iteration
-    double *hp = hr + (size_t)a.hmax * 3;        // hmax * 3: p of every halo node
-    int *hn = (int *)(hp + (size_t)a.hmax * 3);  // hmax
+    // halo = every block column this CTA's rows touch: its own rows first (entry i = local row i), then the foreign nodes.
+    // r and p of the foreign nodes are advanced locally each iteration; p of the own rows is mirrored from registers.
+    // Component-major (x[hmax], y[hmax], z[hmax]): consecutive lanes touch consecutive doubles, no bank conflicts.
+    const int hs = a.hmax;
+    double *hr = (double *)dyn_smem;        // 3 * hmax: r of the halo nodes
+    double *hp = hr + (size_t)hs * 3;       // 3 * hmax: p of the halo nodes
+    double *m8 = hp + (size_t)hs * 3;       // 9 * blockDim: every thread's ninth block, component-major
+    int *lc8 = (int *)(m8 + 9 * blockDim.x);  // blockDim: its local column
+    int *hn = lc8 + blockDim.x;             // hmax: node ids
+    const int n_own = min(W, (int)max(0ll, a.n_slices - (long long)cb * W)) * 32;
     const int h0 = a.halo_ptr[cb], nh = a.halo_ptr[cb + 1] - h0;
     unsigned epoch = 0;
 
@@ -303,21 +414,24 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     const bool sys_on = !sh.done[s];
 
     // the row's blocks and local column indices, once, into registers
-    double m[F_J][9];
-    int lc[F_J];
+    double m[F_JR][9];
+    int lc[F_JR];
     int w = 0;
 #pragma unroll
-    for (int jj = 0; jj < F_J; jj++) {
+    for (int jj = 0; jj < F_JR; jj++) {
         lc[jj] = 0;
 #pragma unroll
         for (int q = 0; q < 9; q++) m[jj][q] = 0.0;
     }
+    lc8[threadIdx.x] = 0;
+#pragma unroll
+    for (int q = 0; q < 9; q++) m8[q * blockDim.x + threadIdx.x] = 0.0;
     if (have && sys_on) {
         const int q0 = a.slice_ptr[sl];
         w = (a.slice_ptr[sl + 1] - q0) >> 5;
         const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288 + (rloc & 31);
 #pragma unroll
-        for (int jj = 0; jj < F_J; jj++) {
+        for (int jj = 0; jj < F_JR; jj++) {
             const int j = 2 * jj + half;
             if (j < w) {
                 lc[jj] = a.lcol[q0 + j * 32 + (rloc & 31)];
@@ -325,19 +439,31 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 for (int q = 0; q < 9; q++) m[jj][q] = v[288 * j + 32 * q];
             }
         }
+        const int j8 = 2 * F_JR + half;
+        if (j8 < w) {
+            lc8[threadIdx.x] = a.lcol[q0 + j8 * 32 + (rloc & 31)];
+#pragma unroll
+            for (int q = 0; q < 9; q++) m8[q * blockDim.x + threadIdx.x] = v[288 * j8 + 32 * q];
+        }
     }
     for (int h = threadIdx.x; h < nh; h += blockDim.x) hn[h] = a.halo_nodes[h0 + h];
     __syncthreads();
 
-    // the only vector that travels between CTAs: Ap of the iteration, two generations
+    // the only vector that travels between CTAs: Ap of the iteration, two generations.  The fourth word of a row is its
+    // epoch tag -- (launch number << 32) | iteration -- written and read with the row as ONE 32-byte access (STG.256 /
+    // LDG.256 on one L2 sector), so a reader recognises a row that has not arrived yet and reads it again: nothing has
+    // to order the rows against the all-reduce of the iteration (see fused_fx_allreduce).  The launch number keeps a row
+    // left by an earlier CG solve at the same iteration from passing.
     double4 *const A_0 = (double4 *)(a.Ap + s * vstride), *const A_1 = (double4 *)(a.Ap1 + s * vstride);
+    const long long tag_base = (long long)a.launch_seq << 32;
+    auto tag_of = [&](long long iter) { return __longlong_as_double(tag_base | (long long)(unsigned)iter); };
     // r_0 = b and p = 0 for this CTA's halo nodes
     if (sys_on) {
         const double4 *b4 = (const double4 *)(a.b + s * vstride);
         for (int h = threadIdx.x; h < nh; h += blockDim.x) {
             const double4 bv = b4[hn[h]];
-            hr[3 * h] = bv.x; hr[3 * h + 1] = bv.y; hr[3 * h + 2] = bv.z;
-            hp[3 * h] = 0.0; hp[3 * h + 1] = 0.0; hp[3 * h + 2] = 0.0;
+            hr[h] = bv.x; hr[hs + h] = bv.y; hr[2 * hs + h] = bv.z;
+            hp[h] = 0.0; hp[hs + h] = 0.0; hp[2 * hs + h] = 0.0;
         }
     }
     double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, y0 = 0, y1 = 0, y2 = 0;
@@ -346,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
         const double4 bv = ((const double4 *)(a.b + s * vstride))[row];
         r0 = bv.x; r1 = bv.y; r2 = bv.z;
         if (owner) {
-            A_1[row] = make_double4(0.0, 0.0, 0.0, 0.0);  // generation "-1": Ap = 0 makes iteration 0 the general case (alpha = beta = 0)
+            st_node(A_1 + row, 0.0, 0.0, 0.0, tag_of(0));  // generation "-1": Ap = 0 makes iteration 0 the general case (alpha = beta = 0)
             acc = r0 * r0 + r1 * r1 + r2 * r2;
         }
     }
@@ -360,14 +486,15 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     });
 
 #ifdef JF_CG_TIMING
-    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    long long tacc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
     int cur = 0;
     unsigned light_target = 0;  // arrivals expected at the light barrier so far (thread 0)
-    unsigned xe = 0;            // iterations reduced through the fixed-point accumulators so far
+    unsigned xe = 0;  // iterations reduced through the fixed-point accumulators so far
+    FxPrev fx_prev;
     double4 pre[F_HALO_BATCH];  // Ap of the previous iteration at this thread's first-round halo nodes (generation "-1": 0)
 #pragma unroll
-    for (int k = 0; k < F_HALO_BATCH; k++) pre[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int k = 0; k < F_HALO_BATCH; k++) pre[k] = make_double4(0.0, 0.0, 0.0, tag_of(0));
     for (long long it = 1; it <= a.maxiter; it++) {
         int all = 1;
         for (int q = 0; q < a.n_sys; q++) all &= sh.done[q];
@@ -381,28 +508,8 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             double4 *An = cur ? A_1 : A_0;        // this iteration's
             // ---- halo: r_j -= alpha Ap_j ; p_j = r_j + beta p_j, once per distinct block column, r and p kept here.
             // The first round's Ap_j were requested right after the barrier (below), while the sums were collected.
-            for (int hb = threadIdx.x; hb < nh; hb += F_HALO_BATCH * blockDim.x) {
-                double4 av[F_HALO_BATCH];
-#pragma unroll
-                for (int k = 0; k < F_HALO_BATCH; k++) {
-                    const int h = hb + k * blockDim.x;
-                    av[k] = (hb == (int)threadIdx.x && a.prefetch) ? pre[k] : ld_node_l2(Ao + hn[h < nh ? h : hb]);
-                }
-#pragma unroll
-                for (int k = 0; k < F_HALO_BATCH; k++) {
-                    const int h = hb + k * blockDim.x;
-                    if (h < nh) {
-                        const double rx = fma(-alpha, av[k].x, hr[3 * h]), ry = fma(-alpha, av[k].y, hr[3 * h + 1]),
-                                     rz = fma(-alpha, av[k].z, hr[3 * h + 2]);
-                        hr[3 * h] = rx; hr[3 * h + 1] = ry; hr[3 * h + 2] = rz;
-                        hp[3 * h] = fma(beta, hp[3 * h], rx);
-                        hp[3 * h + 1] = fma(beta, hp[3 * h + 1], ry);
-                        hp[3 * h + 2] = fma(beta, hp[3 * h + 2], rz);
-                    }
-                }
-            }
-            FMARK(1);
-            // ---- own row: the deferred updates of the previous iteration ------------------------------------
+            const long long expect = tag_base | (long long)(unsigned)(it - 1);
+            // ---- own row: the deferred updates of the previous iteration (first: it ends the life of y) ------
             if (have) {
                 x0 = fma(alpha, p0, x0);
                 x1 = fma(alpha, p1, x1);
@@ -413,24 +520,79 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 p0 = fma(beta, p0, r0);
                 p1 = fma(beta, p1, r1);
                 p2 = fma(beta, p2, r2);
+                if (half == 0) {  // the row's p for the CTA's own block columns: straight from the registers
+                    hp[rloc] = p0;
+                    hp[hs + rloc] = p1;
+                    hp[2 * hs + rloc] = p2;
+                }
             }
+            // (the shared-memory loads of a stage are issued before its first store: hr and hp could alias for all the
+            //  compiler knows, and a load placed behind a store would wait for it)
+            for (int hb = n_own + threadIdx.x; hb < nh; hb += F_HALO_BATCH * blockDim.x) {
+                double4 av[F_HALO_BATCH];
+                double rn[F_HALO_BATCH][3], po[F_HALO_BATCH][3];
+                int hh[F_HALO_BATCH];
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++) {
+                    const int h = hb + k * blockDim.x;
+                    hh[k] = h < nh ? h : hb;
+                    av[k] = (hb == n_own + (int)threadIdx.x && a.prefetch) ? pre[k] : ld_node_l2(Ao + hn[hh[k]]);
+                }
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) rn[k][q] = hr[q * hs + hh[k]];
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++) {
+                    while (__double_as_longlong(av[k].w) != expect) {  // not there yet (rare): read again
+                        av[k] = ld_node_l2(Ao + hn[hh[k]]);
+#ifdef JF_CG_TIMING
+                        if (threadIdx.x == 32) tacc[12]++;
+#endif
+                    }
+                    rn[k][0] = fma(-alpha, av[k].x, rn[k][0]);
+                    rn[k][1] = fma(-alpha, av[k].y, rn[k][1]);
+                    rn[k][2] = fma(-alpha, av[k].z, rn[k][2]);
+                }
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) po[k][q] = hp[q * hs + hh[k]];
+#pragma unroll
+                for (int k = 0; k < F_HALO_BATCH; k++) {
+                    if (hb + k * (int)blockDim.x < nh) {
+#pragma unroll
+                        for (int q = 0; q < 3; q++) {
+                            hr[q * hs + hh[k]] = rn[k][q];
+                            hp[q * hs + hh[k]] = fma(beta, po[k][q], rn[k][q]);
+                        }
+                    }
+                }
+            }
+            FMARK(1);
             __syncthreads();
             // ---- block row: Ap_i = sum_j K_ij p_j ----------------------------------------------------------------
             if (have) {
                 y0 = y1 = y2 = 0.0;
+                // no test on the slice width here: absent blocks are zero with column 0, and straight-line code lets the
+                // loads of the next blocks travel under the multiply-adds of the current one
 #pragma unroll
-                for (int jj = 0; jj < F_J; jj++) {
-                    if (2 * jj < w) {
-                        const double *pj = hp + 3 * lc[jj];
-                        const double px = pj[0], py = pj[1], pz = pj[2];
-                        JF_BLOCK_FMA(m[jj], 1, px, py, pz)
-                    }
+                for (int jj = 0; jj < F_JR; jj++) {
+                    const double *pj = hp + lc[jj];
+                    const double px = pj[0], py = pj[hs], pz = pj[2 * hs];
+                    JF_BLOCK_FMA(m[jj], 1, px, py, pz)
+                }
+                if (2 * F_JR < w) {  // the slice is 17 or 18 blocks wide: the ninth block from shared memory
+                    const double *pj = hp + lc8[threadIdx.x];
+                    const double px = pj[0], py = pj[hs], pz = pj[2 * hs];
+                    const double *m8t = m8 + threadIdx.x;
+                    JF_BLOCK_FMA(m8t, blockDim.x, px, py, pz)
                 }
                 y0 += __shfl_xor_sync(0xffffffffu, y0, 16);
                 y1 += __shfl_xor_sync(0xffffffffu, y1, 16);
                 y2 += __shfl_xor_sync(0xffffffffu, y2, 16);
                 if (owner) {
-                    An[row] = make_double4(y0, y1, y2, 0.0);
+                    st_node(An + row, y0, y1, y2, tag_of(it));  // ONE 32-byte store: row and tag arrive together
                     a0 = p0 * y0 + p1 * y1 + p2 * y2;
                     a1 = r0 * y0 + r1 * y1 + r2 * y2;
                     a2 = y0 * y0 + y1 * y1 + y2 * y2;
@@ -446,24 +608,8 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             sh.warp[2][s][warp] = a2;
         }
         FMARK(2);
-        auto update = [&](int ss, double pAp, double rAp, double ApAp) {
-            if (sh.done[ss]) return;
-            const double rho = sh.rho[ss];
-            const double alpha = rho / pAp;
-            const double rsnew = fma(alpha * alpha, ApAp, fma(-2.0 * alpha, rAp, rho));  // r'.r' without a second pass
-            sh.alpha[ss] = alpha;
-            sh.iters[ss] = (int)it;
-            if (rsnew < a.tol * sh.normb[ss] || it == a.maxiter || !(rsnew > 0.0)) {
-                sh.done[ss] = 1;  // the pending x += alpha p is applied after the loop
-            } else {
-                sh.beta[ss] = rsnew / rho;
-                sh.rho[ss] = rsnew;
-            }
-            int e0 = 0, e2 = 0;  // units of the next iteration's fixed-point sums
-            const bool ok = fx_exponent_ok(pAp, &e0) & fx_exponent_ok(ApAp, &e2);
-            sh.expo[0] = e0;
-            sh.expo[1] = e2;
-            sh.scale_ok = ok;
+        auto update = [&](int ss, double pAp, double rAp, double ApAp, int ln) {
+            fused_update_scalars(sh, ss, pAp, rAp, ApAp, ln, it, a.maxiter, a.tol, true, 0);
         };
         auto prefetch_halo = [&]() {
             // the next iteration's first round of halo loads (this iteration's Ap) travels while the scalars are formed
@@ -471,29 +617,30 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 const double4 *An_c = cur ? A_1 : A_0;
 #pragma unroll
                 for (int k = 0; k < F_HALO_BATCH; k++) {
-                    const int h = (int)threadIdx.x + k * (int)blockDim.x;
+                    const int h = n_own + (int)threadIdx.x + k * (int)blockDim.x;
                     pre[k] = ld_node_l2(An_c + hn[h < nh ? h : 0]);
                 }
             }
         };
         if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {  // the same decision in every CTA: scale_ok comes from shared totals
-            fused_fx_allreduce<5>(a, grid, sh, epoch, xe, light_target, update, prefetch_halo FT_PASS);
+            fused_fx_allreduce<5>(a, sh, epoch, xe, fx_prev, light_target, a.fenced != 0, it, true, 0, update, prefetch_halo FT_PASS);
         } else {
-            const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+            const SlotCounters sc = fused_slot_allreduce<5>(a, &sh, epoch, light_target, it, true, 0);
+            epoch = sc.epoch;
+            light_target = sc.light_target;
             prefetch_halo();
-            fused_collect<3, 5>(a, sh, part, update);
-            FMARK(8);
+            FMARK(7);
         }
         cur ^= 1;
     }
 #ifdef JF_CG_TIMING
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 32) {
         const double n = sh.iters[0] > 0 ? sh.iters[0] : 1;
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        printf("cgt cta %3d sm %3u nh %3d iters %4d | top %5.0f halo %5.0f spmv %5.0f | prep %5.0f fence %5.0f red+poll1 %5.0f pollwait %5.0f post %5.0f slot %5.0f | polls %.2f\n",
+        printf("cgt cta %d sm %u nh %d iters %d | top %.0f halo %.0f spmv %.0f | sync_a %.0f fence %.0f words %.0f redpoll %.0f arrive %.0f decode %.0f update %.0f sync_b %.0f | polls %.2f retries %.3f\n",
                blockIdx.x, smid, nh, sh.iters[0], tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n,
-               tacc[7] / n, tacc[8] / n, tacc[9] / n);
+               tacc[10] / n, tacc[11] / n, tacc[8] / n, tacc[7] / n, tacc[9] / n, tacc[12] / n);
     }
 #endif
 
@@ -593,6 +740,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
 
     unsigned light_target = 0;
     unsigned xe = 0;
+    FxPrev fx_prev;
     int cur = 0;
     for (long long it = 1; it <= a.maxiter; it++) {
         int all = 1;
@@ -692,36 +840,19 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
                 sh.warp[2][s][warp] = a2;
             }
         }
-        auto update = [&](int ss, double pAp, double rAp, double ApAp) {
-            if (sh.done[ss]) return;
-            const double rho = sh.rho[ss];
-            const double alpha = rho / pAp;
-            const double rsnew = fma(alpha * alpha, ApAp, fma(-2.0 * alpha, rAp, rho));
-            sh.alpha[ss] = alpha;
-            sh.iters[ss] = (int)it;
-            sh.lastcur[ss] = cur;  // generation that holds this iteration's p
-            if (rsnew < a.tol * sh.normb[ss] || it == a.maxiter || !(rsnew > 0.0)) {
-                sh.done[ss] = 1;
-            } else {
-                sh.beta[ss] = rsnew / rho;
-                sh.rho[ss] = rsnew;
-            }
-            if (a.n_sys == 1) {  // units of the next iteration's fixed-point sums
-                int e0 = 0, e2 = 0;
-                const bool ok = fx_exponent_ok(pAp, &e0) & fx_exponent_ok(ApAp, &e2);
-                sh.expo[0] = e0;
-                sh.expo[1] = e2;
-                sh.scale_ok = ok;
-            }
+        auto update = [&](int ss, double pAp, double rAp, double ApAp, int ln) {
+            fused_update_scalars(sh, ss, pAp, rAp, ApAp, ln, it, a.maxiter, a.tol, a.n_sys == 1, cur);
         };
         if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {
 #ifdef JF_CG_TIMING
-            long long tacc[10], tlast = 0;
+            long long tacc[14], tlast = 0;
 #endif
-            fused_fx_allreduce<10>(a, grid, sh, epoch, xe, light_target, update, [] {} FT_PASS);
+            // rows of r, p and Ap cross CTAs here and carry no tag: always the fenced ordering
+            fused_fx_allreduce<10>(a, sh, epoch, xe, fx_prev, light_target, true, it, a.n_sys == 1, cur, update, [] {} FT_PASS);
         } else {
-            const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
-            fused_collect<3, 10>(a, sh, part, update);
+            const SlotCounters sc = fused_slot_allreduce<10>(a, &sh, epoch, light_target, it, a.n_sys == 1, cur);
+            epoch = sc.epoch;
+            light_target = sc.light_target;
         }
         cur ^= 1;
     }
@@ -770,7 +901,7 @@ int jf_cg_fused_configure(jf_ctx *c) {
     c->cg_fused = 0;
     // the collect keeps five partial sums per lane in registers: at most 160 CTAs (B200: 148 SMs)
     if (c->cg_resident != 2 || c->n_sys > F_MAX_SYS || c->cg_grid > 160 || getenv("JF_CG_CLASSIC")) return 0;
-    const size_t smem = (size_t)c->cg_hmax * (6 * sizeof(double) + sizeof(int));
+    const size_t smem = (size_t)c->cg_hmax * (6 * sizeof(double) + sizeof(int)) + (size_t)c->cg_res_warps * 64 * (9 * sizeof(double) + sizeof(int));
     JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_kernel, c->cg_res_warps * 64, smem));
@@ -820,6 +951,8 @@ int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
     const bool no_prefetch = getenv("JF_CG_NO_PREFETCH") != nullptr, cg_sync = getenv("JF_CG_CGSYNC") != nullptr,
                slot_sums = getenv("JF_CG_SLOT_SUMS") != nullptr;
     a.prefetch = !no_prefetch;
+    a.fenced = getenv("JF_CG_FENCED") != nullptr;  // order the Ap rows by fence/acquire instead of relying on their tags
+    a.launch_seq = (int)(++c->cg_launch_seq & 0x7fffffff);
     a.light_barrier = !cg_sync;
     a.exact_sums = !slot_sums && !cg_sync;
     a.fx_test = getenv("JF_FX_TEST_OVERFLOW") ? atoi(getenv("JF_FX_TEST_OVERFLOW")) : 0;

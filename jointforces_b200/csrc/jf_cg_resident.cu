@@ -409,13 +409,28 @@ int jf_cg_resident_configure(jf_ctx *c) {
         for (int64_t cb = lo; cb < hi; cb++) {
             const int64_t s0 = cb * W, s1 = std::min<int64_t>(c->n_slices, s0 + W);
             const int64_t q0 = c->h_slice_ptr[s0], q1 = c->h_slice_ptr[s1];
+            // the CTA's own rows first, in row order (entry i = local row i; jf_cg_fused_kernel keeps their p in
+            // registers and only mirrors it here), then the foreign block columns, sorted
             std::vector<int32_t> &tmp = lists[cb];
-            tmp.assign(c->h_sell_col.begin() + q0, c->h_sell_col.begin() + q1);
-            std::sort(tmp.begin(), tmp.end());
-            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            const int32_t own0 = (int32_t)(s0 * JF_SLICE), own1 = (int32_t)(s1 * JF_SLICE);
+            std::vector<int32_t> foreign;
+            for (int64_t q = q0; q < q1; q++) {
+                const int32_t col = c->h_sell_col[q];
+                if (col < own0 || col >= own1) foreign.push_back(col);
+            }
+            std::sort(foreign.begin(), foreign.end());
+            foreign.erase(std::unique(foreign.begin(), foreign.end()), foreign.end());
+            tmp.resize((size_t)(own1 - own0));
+            for (int32_t i = own0; i < own1; i++) tmp[i - own0] = i;
+            tmp.insert(tmp.end(), foreign.begin(), foreign.end());
             if (tmp.size() > 65535) continue;
-            for (int64_t q = q0; q < q1; q++)
-                lcol[q] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), c->h_sell_col[q]) - tmp.begin());
+            const int32_t n_own = own1 - own0;
+            for (int64_t q = q0; q < q1; q++) {
+                const int32_t col = c->h_sell_col[q];
+                lcol[q] = (col >= own0 && col < own1)
+                              ? (uint16_t)(col - own0)
+                              : (uint16_t)(n_own + (std::lower_bound(foreign.begin(), foreign.end(), col) - foreign.begin()));
+            }
         }
     }, 8);
     for (int cb = 0; cb < ctas; cb++) {

@@ -39,6 +39,8 @@ def lib():
         L.so_relax.argtypes = [C.c_int, C.c_int, _dp, _ip, _bp, _dp, _dp, C.c_int, _dp] + [C.c_double] * 4 + \
                               [C.c_double, C.c_int, C.c_double, _dp, _ip, _dp, _dp, C.c_int, C.c_double]
         L.so_relax.restype = C.c_int
+        L.so_cg_variants.argtypes = [C.c_int, C.c_int, _dp, _ip, _bp, _dp, _dp, C.c_int, _dp] + [C.c_double] * 5 + [_ip]
+        L.so_cg_variants.restype = None
         L.so_pattern_nnz.argtypes = [C.c_int, C.c_int, _ip, _bp]
         L.so_pattern_nnz.restype = C.c_int64
         L.so_assemble.argtypes = [C.c_int, C.c_int, _dp, _ip, _bp, _dp, C.c_int, _dp] + [C.c_double] * 4 + \
@@ -106,3 +108,14 @@ def relax(nodes, tets, movable, f_target, U0, beams, material, step, max_iter, c
                        int(max_iter), float(conv_crit), relrec, cgit, forces, timing, int(nthreads), float(cg_tol))
     return dict(U=U, forces=forces, relrec=relrec[: n + 1].copy(), cg_iters=cgit[:n].copy(), n_iter=n,
                 t_element=timing[0], t_cg=timing[1])
+
+
+def cg_variants(nodes, tets, movable, f_target, U, beams, material, tol=1e-5):
+    """CG iteration counts of one Newton step at displacements U under three arithmetic variants (plain double as the
+    oracle, fused multiply-add + pairwise sums as a GPU, long double): tools/cg_precision_study.py."""
+    nodes, tets, beams, U = _c(nodes, np.float64), _c(tets, np.int32), _c(beams, np.float64), _c(U, np.float64)
+    ft = _c(np.nan_to_num(np.asarray(f_target, dtype=np.float64)), np.float64)
+    it = np.zeros(3, np.int32)
+    lib().so_cg_variants(len(nodes), len(tets), nodes, tets, _c(movable, np.uint8), ft, U, len(beams), beams,
+                         *map(float, material), float(tol), it)
+    return dict(double_plain=int(it[0]), double_fma_pairwise=int(it[1]), long_double=int(it[2]))

@@ -437,3 +437,100 @@ double so_assemble(int N, int T, const double *nodes, const int32_t *tets, const
     pattern_free(p);
     return e;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Diagnostic (tools/cg_precision_study.py): how many iterations does the SAME CG (A13) take on the SAME system
+ * when only the floating-point evaluation of its sums changes?  variant 0: this file's (plain double, products and
+ * sums rounded separately, sequential sums); 1: fused multiply-adds and pairwise (tree) dot products, the way a GPU
+ * evaluates them; 2: everything in long double (64-bit mantissa).  CG's convergence is delayed by rounding errors
+ * (loss of orthogonality); the more exact the arithmetic, the fewer iterations to the same residual.
+ * ------------------------------------------------------------------------------------------- */
+static double dot_pairwise(const double *a, const double *b, int n) {
+    if (n <= 32) {
+        double acc = 0.0;
+        for (int i = 0; i < n; i++) acc = fma(a[i], b[i], acc);
+        return acc;
+    }
+    int h = n / 2;
+    return dot_pairwise(a, b, h) + dot_pairwise(a + h, b + h, n - h);
+}
+
+static int cg_variant(const so_pattern *p, const double *val, const double *b, int maxiter, double tol, int variant) {
+    int n = 3 * p->N;
+    if (variant == 2) {
+        long double *x = calloc(n, sizeof(long double)), *r = malloc(n * sizeof(long double)), *pp = malloc(n * sizeof(long double)),
+                    *Ap = malloc(n * sizeof(long double));
+        long double normb = 0;
+        for (int i = 0; i < n; i++) { r[i] = pp[i] = b[i]; normb += (long double)b[i] * b[i]; }
+        long double resid = normb;
+        int it = 0;
+        if (normb > 0)
+            for (it = 1; it <= maxiter; it++) {
+                long double pAp = 0;
+#pragma omp parallel for schedule(static) reduction(+ : pAp)
+                for (int i = 0; i < n; i++) {
+                    long double acc = 0;
+                    for (int64_t j = p->rowptr[i]; j < p->rowptr[i + 1]; j++) acc += (long double)val[j] * pp[p->col[j]];
+                    Ap[i] = acc;
+                    pAp += pp[i] * acc;
+                }
+                long double alpha = resid / pAp, rsnew = 0;
+                for (int i = 0; i < n; i++) { x[i] += alpha * pp[i]; r[i] -= alpha * Ap[i]; rsnew += r[i] * r[i]; }
+                if (rsnew < tol * normb) break;
+                long double beta = rsnew / resid;
+                for (int i = 0; i < n; i++) pp[i] = r[i] + beta * pp[i];
+                resid = rsnew;
+            }
+        free(x); free(r); free(pp); free(Ap);
+        return it > maxiter ? maxiter : it;
+    }
+    double *x = calloc(n, sizeof(double)), *r = malloc(n * sizeof(double)), *pp = malloc(n * sizeof(double)), *Ap = malloc(n * sizeof(double));
+    memcpy(r, b, n * sizeof(double));
+    memcpy(pp, b, n * sizeof(double));
+    double normb = variant ? dot_pairwise(b, b, n) : dot(n, b, b);
+    double resid = normb;
+    int it = 0;
+    if (normb > 0)
+        for (it = 1; it <= maxiter; it++) {
+            if (variant) {
+#pragma omp parallel for schedule(static)
+                for (int i = 0; i < n; i++) {
+                    double acc = 0.0;
+                    for (int64_t j = p->rowptr[i]; j < p->rowptr[i + 1]; j++) acc = fma(val[j], pp[p->col[j]], acc);
+                    Ap[i] = acc;
+                }
+            } else {
+                spmv(p, val, pp, Ap);
+            }
+            double alpha = resid / (variant ? dot_pairwise(pp, Ap, n) : dot(n, pp, Ap));
+            for (int i = 0; i < n; i++) {
+                if (variant) { x[i] = fma(alpha, pp[i], x[i]); r[i] = fma(-alpha, Ap[i], r[i]); }
+                else { x[i] += alpha * pp[i]; r[i] -= alpha * Ap[i]; }
+            }
+            double rsnew = variant ? dot_pairwise(r, r, n) : dot(n, r, r);
+            if (rsnew < tol * normb) break;
+            double beta = rsnew / resid;
+            for (int i = 0; i < n; i++) pp[i] = variant ? fma(beta, pp[i], r[i]) : r[i] + beta * pp[i];
+            resid = rsnew;
+        }
+    free(x); free(r); free(pp); free(Ap);
+    return it > maxiter ? maxiter : it;
+}
+
+/* CG iteration counts of the three arithmetic variants for the Newton step at displacements U */
+void so_cg_variants(int N, int T, const double *nodes, const int32_t *tets, const uint8_t *movable, const double *f_target,
+                    const double *U, int Nb, const double *beams, double k, double d0, double ls, double ds, double tol,
+                    int32_t *iters /* [3] */) {
+    so_material mat = {k, d0, ls, ds};
+    so_pattern *p = pattern_build(N, T, tets, movable);
+    double *Phi = malloc(sizeof(double) * 12 * (size_t)T), *V = malloc(sizeof(double) * (size_t)T), *E = malloc(sizeof(double) * (size_t)T);
+    double *f_el = malloc(sizeof(double) * 12 * (size_t)T), *K_el = malloc(sizeof(double) * 144 * (size_t)T);
+    double *val = malloc(sizeof(double) * (size_t)p->nnz), *forces = malloc(sizeof(double) * 3 * (size_t)N), *ff = malloc(sizeof(double) * 3 * (size_t)N);
+    so_shape_tensors(T, nodes, tets, Phi, V);
+    update_f_and_K(p, tets, U, Phi, V, Nb, beams, &mat, E, f_el, K_el, forces, val);
+    for (int i = 0; i < N; i++)
+        for (int c = 0; c < 3; c++) ff[3 * i + c] = movable[i] ? forces[3 * i + c] - f_target[3 * i + c] : 0.0;
+    for (int v = 0; v < 3; v++) iters[v] = cg_variant(p, val, ff, 3 * N, tol, v);
+    free(Phi); free(V); free(E); free(f_el); free(K_el); free(val); free(forces); free(ff);
+    pattern_free(p);
+}

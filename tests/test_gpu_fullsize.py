@@ -98,14 +98,19 @@ def test_fullsize_relaxation_scales_with_load_for_linear_material(big_case, beam
 import os
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-# name -> (kernel the default path must take: (cg_resident, cg_fused), tolerance on the CG iteration total)
+# name -> (kernel the default path must take: (cg_resident, cg_fused), allowed relative difference of the CG iteration total).
+# The CUDA kernels need 0.6-3 % FEWER iterations than the oracle's C port, the classic two-reduction kernels exactly like
+# the single-reduction ones (tools/cg_iter_bias.py): CG's convergence is delayed by rounding, and the kernels round
+# less (fused multiply-adds, tree sums, exact all-reduce).  The oracle's own CG on its own matrix shows the same shift when
+# only its sums are evaluated that way, and more in long double (tools/cg_precision_study.py: 1005 / 984 / 946 iterations
+# at 10 kPa, 825 / 807 / 804 at 100 Pa); the displacements agree to 1e-5 regardless.  Hence an asymmetric window.
 FULL_CASES = {
-    "cfg2_full": ((2, 1), 0.02),   # register-resident single-reduction kernel (the bench headline)
-    "cfg3_rowA": ((2, 1), 0.02),
-    "cfg3_rowB": ((2, 1), 0.02),
-    "cfg4_full": ((0, 2), 0.02),   # streaming single-reduction kernel
-    "cfg5_loose": ((0, 0), 0.02),  # plain HBM-bound streaming kernel (roofline_large of bench.py)
-    "cfg5_tight": ((0, 0), 0.02),
+    "cfg2_full": ((2, 1), (-0.04, 0.01)),   # register-resident single-reduction kernel (the bench headline)
+    "cfg3_rowA": ((2, 1), (-0.04, 0.01)),
+    "cfg3_rowB": ((2, 1), (-0.05, 0.01)),
+    "cfg4_full": ((0, 2), (-0.05, 0.01)),   # streaming single-reduction kernel
+    "cfg5_loose": ((0, 0), (-0.05, 0.01)),  # plain HBM-bound streaming kernel (roofline_large of bench.py)
+    "cfg5_tight": ((0, 0), (-0.05, 0.01)),
 }
 
 
@@ -153,7 +158,7 @@ def test_fullsize_relaxation_matches_oracle_fixture(name, beams, capsys):
     assert err < 1e-4, err
     assert abs(np.linalg.norm(U) / float(g["U_norm"]) - 1) < 1e-4
     assert np.allclose(relrec[0][:, 1], g["relrec"][:, 1], rtol=1e-4)
-    assert abs(int(d.sum())) <= cg_tol_total * g["cg_iters"].sum()
+    assert cg_tol_total[0] <= d.sum() / g["cg_iters"].sum() <= cg_tol_total[1]
     x, _ = lookup_bins()
     curve = radial_median_curve(coords, U, 100e-6, x)
     ok = ~np.isnan(g["curve"])
