@@ -1,24 +1,37 @@
 #!/usr/bin/env python
 """Benchmark of the relaxation hot path (contract: see the task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1|cfg4|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one complete relaxation (Newton iterations until saenopy's five-energy stop rule) of
-the named BASELINE config on each rank's GPU -- a lookup-table "sim".  Ranks share nothing on the
-data path (independent load cases, weak scaling); the curve rows are gathered over NCCL.
+Default workload ``cfg3`` = BASELINE configs[2], the lookup-table sweep the metric "sims/hour at 1/2/4/8
+B200" is quoted on: collagen12 on the configs[1] mesh (17,612 nodes / 102,744 tets), pressures from
+``np.logspace(-1, 4, 150)``.  One "step" relaxes every fifth pressure of that table (30 solves, all three
+material regimes; five consecutive steps cover the table once) and gathers the 30 curve rows.  STRONG scaling:
+the 30 solves of a step are spread over the N ranks (shared work counter in the process group's store), the
+rows gathered over NCCL at the end of every step.
 
-  value   sims/hour, whole job, device time (CUDA events in the library, max over ranks), inputs
-          (mesh structure, targets, start displacements) resident in HBM when the timed region starts
-  e2e     the same metric through the reference-facing host call (C-ABI jf_solve_boundarycondition
-          behind Solver.solve_boundarycondition): host buffers in, structure build, H2D, relaxation,
-          D2H of displacements/forces, radial curve, gather
+  value   sims/hour, whole job, device time: per step the max over ranks of the CUDA-event time of its
+          relaxations (jf_relax), mesh structure resident in HBM
+  e2e     the same metric through the public call ``run_sweep`` (what ``jf.simulation.distribute_solver``
+          runs): mesh file on disk -> structure build -> H2D -> relaxations -> D2H -> the reference's
+          output folders written -> NCCL gather; wall clock, max over ranks
+
+``--workload cfg2`` (cfg1/cfg4/cfg5) times single solves instead: one step = one complete relaxation on each
+rank's GPU (weak scaling); at N=1 the default run adds that number for configs[1] as ``single_solve``.
+
+``--impl reference``: the reference's CPU implementation of the same workload -- the oracle's C port of the
+saenopy algorithm (saenopy itself cannot be installed here; if ``import saenopy`` works on the
+box it is used instead), run the way the reference runs a sweep (simulation.py:186-187, 218-246): several
+solver processes alive at once, every one a COMPLETE solve, nothing extrapolated.
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -31,10 +44,19 @@ WORKLOADS = {
     # name: (BASELINE config text, length_factor, lf_iso override, material name, pressure)
     "cfg1": ("configs[0]: spherical_inclusion lf=0.2 (lf_iso 0.2), linear K_0=2364, 100 Pa", None, 0.2, "linear2364", 100.0),
     "cfg2": ("configs[1]: spherical_inclusion lf=0.05 (lf_iso 0.1667), collagen12, 100 Pa, single solve", 0.05, None, "collagen12", 100.0),
+    "cfg3": ("configs[2]: collagen12 lookup-table sweep on the configs[1] mesh, np.logspace(-1,4,150); one step = every 5th "
+             "pressure (30 solves), offset rotating with the step", 0.05, None, "collagen12", None),
     "cfg4": ("configs[3]: spherical_inclusion lf=0.03 (lf_iso 0.1), collagen24, 10 kPa", 0.03, None, "collagen24", 10000.0),
     "cfg5": ("configs[4]: spherical_inclusion lf=0.015 (lf_iso 0.05), collagen06, 100 Pa", 0.015, None, "collagen06", 100.0),
 }
 SOLVER = dict(step=0.0033, max_iter=600, conv_crit=0.01)   # reference defaults, simulation.py:81
+TABLE = np.logspace(-1, 4, 150)                             # README.md:101-108
+STRIDE = 5                                                  # pressures per step = 150 / STRIDE
+R_IN, R_OUT = 100 * 10 ** -6, 10000 * 10 ** -6
+
+
+def step_indices(j):
+    return np.arange(j % STRIDE, len(TABLE), STRIDE)
 
 
 def material_of(name):
@@ -49,12 +71,23 @@ def build_case(workload):
     from jointforces_b200.solver import build_beams
     text, lf, lf_iso, matname, pressure = WORKLOADS[workload]
     coords, tets = generate_spherical_inclusion(length_factor=lf or 0.05, lf_iso=lf_iso)
-    r_in, r_out = 100 * 10 ** -6, 10000 * 10 ** -6
-    bc = spherical_boundary_conditions(coords, r_in, r_out, pressure)
+    bc = spherical_boundary_conditions(coords, R_IN, R_OUT, pressure if pressure is not None else 1.0)
     movable = np.any(np.isnan(bc["displacement"]), axis=1)
     mat_dict, mat = material_of(matname)
     return dict(text=text, coords=coords, tets=tets.astype(np.int32), movable=movable, ft=np.nan_to_num(bc["forces"]),
-                bc=bc, mat=mat, mat_dict=mat_dict, matname=matname, pressure=pressure, r_in=r_in, beams=build_beams(300))
+                bc=bc, mat=mat, mat_dict=mat_dict, matname=matname, pressure=pressure, r_in=R_IN, beams=build_beams(300),
+                length_factor=lf or 0.05, lf_iso=lf_iso)
+
+
+def shared_config(case, workload):
+    """The part of the JSON line both arms print identically."""
+    cfg = {"workload": case["text"], "n_nodes": int(len(case["coords"])), "n_tets": int(len(case["tets"])),
+           "material": case["matname"], "solver": SOLVER}
+    if workload == "cfg3":
+        cfg.update(pressures_per_step=int(len(step_indices(0))), table="np.logspace(-1, 4, 150)[(step % 5)::5]")
+    else:
+        cfg.update(pressure_pa=case["pressure"])
+    return cfg
 
 
 class ClockSampler:
@@ -105,6 +138,40 @@ def cg_bytes_per_iteration(info):
     return info["n_blocks"] * 76 + info["n_free"] * (4 + 24 + 24 + 9 * 24)
 
 
+def cg_kernel_name(info):
+    if info.get("cg_fused") == 1:
+        return "jf_cg_fused_kernel"
+    if info.get("cg_fused") == 2:
+        return "jf_cg_fused_stream_kernel"
+    if info["cg_resident"] == 2:
+        return "jf_cg_regres_kernel"
+    if info["cg_resident"] == 1:
+        return "jf_cg_resident_kernel"
+    return "jf_cg_streamhalo_kernel" if info.get("cg_stream_halo") else "jf_cg_stream_kernel"
+
+
+def roofline_of(info, st, peaks, peak_kind, workload):
+    """The dominant kernel (CG).  Where the matrix is register/shared-memory resident the kernel is bound by the latency
+    of its per-iteration all-reduce, not by HBM: `achieved` is then a RATE of algorithmic bytes (what an HBM-streaming
+    kernel would have to sustain for the same iteration time), `traffic` the DRAM bytes ncu measured for one launch."""
+    by_iter = cg_bytes_per_iteration(info)
+    achieved = by_iter * st["cg_iterations"] / (st["ms_cg"] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "cg_traffic_%s.json" % ("cfg2" if workload == "cfg3" else workload))
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    resident = bool(info["cg_resident"])
+    matrix_mb = info["n_blocks"] * 72 / 1e6
+    return {"bound": "latency" if resident else "hbm", "nominal_bound": "hbm", "kernel": cg_kernel_name(info), "achieved": achieved,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+            "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": by_iter * st["cg_iterations"] / max(1, st["cg_launches"]),
+            "us_per_cg_iteration": st["ms_cg"] * 1e3 / max(1, st["cg_iterations"]),
+            "achieved_is": ("a rate of algorithmic bytes: the %.0f MB matrix is staged once per CG solve into registers / shared "
+                            "memory, DRAM is idle (`traffic`); the iteration is bound by its grid-wide all-reduce. "
+                            "roofline_large is the HBM-bound regime" % matrix_mb) if resident else "HBM traffic (matrix streamed)"}
+
+
 def hbm_regime_leg(device, peaks):
     """The same CG kernel family where the matrix cannot be cache resident (BASELINE configs[4] size):
     a structured graded shell mesh (502,968 nodes / 2,989,980 tets), one evaluation, CG launches of exactly
@@ -114,7 +181,7 @@ def hbm_regime_leg(device, peaks):
     from jointforces_b200.simulation import spherical_boundary_conditions
     from jointforces_b200.solver import build_beams
     coords, tets = generate_spherical_inclusion(lf_iso=0.05, method="icoshell")
-    bc = spherical_boundary_conditions(coords, 100 * 10 ** -6, 10000 * 10 ** -6, 100.0)
+    bc = spherical_boundary_conditions(coords, R_IN, R_OUT, 100.0)
     movable = np.any(np.isnan(bc["displacement"]), axis=1)
     m = materials.collagen06
     with _lib.Context(coords, tets.astype(np.int32), movable, n_sys=1, beams=build_beams(300), device=device) as ctx:
@@ -127,71 +194,197 @@ def hbm_regime_leg(device, peaks):
         ctx.reset_stats()
         reps = 5
         for _ in range(reps):
-            it = ctx.cg(1e-30, 50)
+            ctx.cg(1e-30, 50)
         st, info = ctx.stats(), ctx.info()
     by = cg_bytes_per_iteration(info)
     achieved = by * 50 * reps / (st["ms_cg"] * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "jf_cg_streamhalo_kernel" if info.get("cg_stream_halo") else "jf_cg_stream_kernel", "workload": "configs[4]-size icoshell mesh, %d nodes / %d tets, "
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "cg_traffic_large.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    return {"bound": "hbm", "kernel": cg_kernel_name(info), "workload": "configs[4]-size icoshell mesh, %d nodes / %d tets, "
             "collagen06; matrix %.0f MB" % (info["n_nodes"], info["n_tets"], info["n_blocks"] * 72 / 1e6),
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "us_per_cg_iteration": st["ms_cg"] * 1e3 / (50 * reps), "algorithmic_bytes_per_launch": by * 50,
-            "traffic": None,
-            "tet_updates_per_s": st["tet_updates"] / (st["ms_element"] * 1e-3) if st["ms_element"] > 0 else None}
+            "traffic": traffic}
 
 
-def cpu_sample(case, newton_steps, threads):
-    """The oracle's C port on the host cores, bounded to `newton_steps` Newton iterations."""
-    from oracle import c_oracle
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU side: complete solves with the oracle (or saenopy where it can be imported)
+# ---------------------------------------------------------------------------------------------------------------------
+def _cpu_solve_worker(args):
+    """One complete relaxation in a worker process.  Returns (seconds, newton steps, cg iterations, kind)."""
+    npz, pressure, mat, threads, want_saenopy = args
+    sys.path.insert(0, ROOT)
+    d = np.load(npz)
+    coords, tets = d["coords"], d["tets"]
+    from jointforces_b200.simulation import spherical_boundary_conditions
+    bc = spherical_boundary_conditions(coords, R_IN, R_OUT, pressure)
     t0 = time.time()
-    r = c_oracle.relax(case["coords"], case["tets"], case["movable"], case["ft"], np.zeros_like(case["coords"]),
-                       case["beams"], case["mat"], SOLVER["step"], newton_steps, SOLVER["conv_crit"], nthreads=threads)
-    return time.time() - t0, r
+    if want_saenopy:
+        import saenopy                                             # the genuine reference path (simulation.py:100-167)
+        from saenopy.materials import SemiAffineFiberMaterial
+        M = saenopy.Solver()
+        M.set_material_model(SemiAffineFiberMaterial(*mat))
+        M.set_nodes(coords)
+        M.set_tetrahedra(tets.astype(np.float64))
+        M.set_boundary_condition(bc["displacement"], bc["forces"])
+        rr = M.solve_boundarycondition(step_size=SOLVER["step"], max_iterations=SOLVER["max_iter"], rel_conv_crit=SOLVER["conv_crit"])
+        return time.time() - t0, len(rr) - 1, -1, "reference"
+    from oracle import c_oracle
+    from oracle.saeno_oracle import build_beams
+    movable = np.any(np.isnan(bc["displacement"]), axis=1)
+    r = c_oracle.relax(coords, tets.astype(np.int32), movable, np.nan_to_num(bc["forces"]), np.zeros_like(coords),
+                       build_beams(300), mat, SOLVER["step"], SOLVER["max_iter"], SOLVER["conv_crit"], nthreads=threads)
+    return time.time() - t0, int(r["n_iter"]), int(r["cg_iters"].sum()), "port"
 
 
-def cpu_full_solve_estimate(r, dt, full_newton, full_cg):
-    """Scale a sample of the first Newton iterations to a full solve: the element/assembly part with the number
-    of evaluations, the CG part with the number of CG iterations (the early Newton steps need fewer CG iterations
-    than the average one, so scaling everything by the Newton count alone would flatter the CPU)."""
-    n_s, cg_s = int(r["n_iter"]), int(r["cg_iters"].sum())
-    t_el, t_cg = float(r["t_element"]), float(r["t_cg"])
-    other = max(0.0, dt - t_el - t_cg)   # pattern build, shape tensors: once per solve
-    return other + t_el * (full_newton + 1) / (n_s + 1) + t_cg * full_cg / max(1, cg_s)
+def saenopy_importable():
+    try:
+        import saenopy  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+class CpuPool:
+    """The reference's sweep shape (simulation.py:186-187, 218-246): `procs` solver processes alive at once, one
+    pressure each; here every process is the oracle's OpenMP C port on cores/procs threads."""
+
+    def __init__(self, case, procs=None):
+        self.cores = os.cpu_count() or 1
+        self.procs = procs or max(1, min(8, self.cores // 8))
+        self.threads = max(1, self.cores // self.procs)
+        self.saenopy = saenopy_importable()
+        self.case = case
+        self.tmp = tempfile.mkdtemp(prefix="jf_cpu_")
+        self.npz = os.path.join(self.tmp, "mesh.npz")
+        np.savez(self.npz, coords=case["coords"], tets=case["tets"])
+        import multiprocessing as mp
+        self.pool = mp.get_context("spawn").Pool(self.procs)
+
+    def wave(self, pressures):
+        """Solve `pressures` (<= procs of them) concurrently; returns (wall seconds, per-solve tuples)."""
+        t0 = time.time()
+        out = self.pool.map(_cpu_solve_worker, [(self.npz, float(p), self.case["mat"], self.threads, self.saenopy) for p in pressures])
+        return time.time() - t0, out
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        shutil.rmtree(self.tmp, ignore_errors=True)
+
+    def describe(self):
+        return ("saenopy %s" % __import__("saenopy").__version__) if self.saenopy else "oracle/saeno_oracle.c (C port, OpenMP)"
+
+
+def wave_pressures(case, workload, j, procs):
+    """The pressures one CPU wave solves: spread evenly over the step's subset (cheap and expensive cases alike)."""
+    if workload != "cfg3":
+        return [case["pressure"]] * procs
+    idx = step_indices(j)
+    pick = idx[np.round(np.linspace(0, len(idx) - 1, procs + 2)[1:-1]).astype(int)] if procs < len(idx) else idx
+    return [float(TABLE[i]) for i in pick]
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  saenopy itself cannot be
-    installed here, so this is the oracle's C port of the same algorithm (kind
-    "port"), on all host threads, each step a bounded sample of the workload."""
+    """--impl reference (rank 0 only): complete CPU solves, several processes alive at once, nothing extrapolated.
+    The number of timed steps is capped by a time budget; `steps` reports what was actually timed."""
     if rank != 0:
         return
     case = build_case(args.workload)
-    cores = os.cpu_count() or 1
-    sample_newton = args.cpu_newton
-    full_newton = args.full_newton
-    for _ in range(args.warmup and 1):
-        cpu_sample(case, 1, cores)
-    times, ests = [], []
-    for _ in range(args.steps):
-        dt, r = cpu_sample(case, sample_newton, cores)
-        times.append(dt)
-        ests.append(cpu_full_solve_estimate(r, dt, full_newton, args.full_cg))
-    est_solve_s = float(np.mean(ests))
-    value = 3600.0 / est_solve_s   # the host cores serve the ranks' solves one after another
-    sample = ("first %d of %d Newton iterations of one solve (%d nodes, %d tets) with oracle/saeno_oracle.c on %d threads, "
-              "%.2f s; element part scaled by evaluations, CG part by CG iterations (%d per solve) -> %.1f s per solve"
-              % (sample_newton, full_newton, len(case["coords"]), len(case["tets"]), cores, float(np.mean(times)),
-                 args.full_cg, est_solve_s))
+    pool = CpuPool(case, args.cpu_procs)
+    budget = args.cpu_budget
+    try:
+        t_start = time.time()
+        walls, solves = [], []
+        j = 0
+        while j < args.steps and (j == 0 or time.time() - t_start + (np.mean(walls) if walls else 0) < budget):
+            wall, out = pool.wave(wave_pressures(case, args.workload, j, pool.procs))
+            walls.append(wall)
+            solves += out
+            j += 1
+    finally:
+        pool.close()
+    n_solves = len(solves)
+    value = n_solves * 3600.0 / float(np.sum(walls))
+    kind = solves[0][3]
+    sample = ("%d complete solves (%d waves of %d processes x %d threads, %s; %.1f s per wave; Newton steps %s)"
+              % (n_solves, len(walls), pool.procs, pool.threads, pool.describe(), float(np.mean(walls)),
+                 sorted({s[1] for s in solves})))
     line = {
         "impl": "reference", "metric": "lookup-table sims/hour", "value": value, "unit": "sims/hour", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": case["text"], "n_nodes": int(len(case["coords"])), "n_tets": int(len(case["tets"])),
-                   "solver": SOLVER, "step_is": "bounded sample: %d Newton iterations" % sample_newton},
-        "cpu_baseline": {"value": value, "unit": "sims/hour", "cores": cores, "kind": "port", "sample": sample},
+        "steps": len(walls), "steps_requested": args.steps, "warmup": 0, "ms_per_step": 1e3 * float(np.mean(walls)),
+        "higher_is_better": True, "scaling": "strong" if args.workload == "cfg3" else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": shared_config(case, args.workload),
+        "note": "every timed step is one wave of complete CPU solves; the number of waves is capped by a %d s budget "
+                "(--cpu-budget), no warm-up wave (nothing to warm: every solve is a cold start)" % budget,
+        "cpu_baseline": {"value": value, "unit": "sims/hour", "cores": pool.cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "sims/hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------------------------------
+def single_solve_legs(case, local, K, W, flush, barrier, world, rank, dist, torch):
+    """Device-timed and end-to-end single relaxations of `case` (one per rank).  Returns a dict of numbers."""
+    from jointforces_b200 import _lib
+    from jointforces_b200.simulation import radial_median_curve, lookup_bins
+    from jointforces_b200.sweep import gather_table
+    x_edges, _ = lookup_bins()
+    ctx = _lib.Context(case["coords"], case["tets"], case["movable"], n_sys=1, beams=case["beams"], device=local)
+    ctx.set_material(*case["mat"])
+    ctx.set_targets(case["ft"])
+    ctx.set_displacements(np.zeros_like(case["coords"]))
+    info = ctx.info()
+
+    def device_step():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.restore_displacements()
+        return ctx.relax(SOLVER["step"], SOLVER["max_iter"], SOLVER["conv_crit"])
+
+    for _ in range(W):
+        device_step()
+    ctx.reset_stats()
+    barrier()
+    t0 = time.time()
+    for _ in range(K):
+        relrec, cgit, n_iter = device_step()
+    barrier()
+    wall = time.time() - t0
+    st = ctx.stats()
+    ctx.close()
+    ms_dev = torch.tensor([st["ms_relax"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_dev, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms_dev.item()) / K
+
+    def e2e_step():
+        out = _lib.solve_boundarycondition(case["coords"], case["tets"], case["movable"], case["ft"],
+                                           np.zeros_like(case["coords"]), case["mat"], SOLVER["step"], SOLVER["max_iter"],
+                                           SOLVER["conv_crit"], beams=case["beams"], device=local)
+        curve = radial_median_curve(case["coords"], out["U"], case["r_in"], x_edges)
+        gather_table([rank], [case["pressure"]], curve[None, :], world, len(curve), device=local)
+        return out
+
+    e2e_step()
+    Ke = min(K, 5)
+    barrier()
+    t0 = time.time()
+    for _ in range(Ke):
+        flush.fill_(1)
+        out = e2e_step()
+    barrier()
+    e2e_ms = torch.tensor([(time.time() - t0) * 1e3 / Ke], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    return dict(info=info, st=st, ms_per_step=ms_per_step, wall_ms=wall * 1e3 / K, e2e_ms=float(e2e_ms.item()), e2e_steps=Ke,
+                h2d=int(out["stats"]["bytes_h2d"]), d2h=int(out["stats"]["bytes_d2h"]), newton=int(n_iter[0]), cg=int(cgit[0].sum()))
 
 
 def main():
@@ -200,12 +393,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-newton", type=int, default=6, help="Newton iterations in the CPU baseline sample")
-    ap.add_argument("--full-newton", type=int, default=86, help="Newton iterations of the full solve (cfg2: 86)")
-    ap.add_argument("--full-cg", type=int, default=68800, help="CG iterations of the full solve (cfg2: ~68,800)")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-procs", type=int, default=0, help="CPU solver processes alive at once (0: cores // 8, at most 8)")
+    ap.add_argument("--cpu-budget", type=float, default=200.0, help="seconds of CPU solves in the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm-leg", action="store_true", help="skip the large-mesh (HBM-bound) CG roofline leg")
+    ap.add_argument("--no-single", action="store_true", help="skip the configs[1] single-solve leg of the default run")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,9 +410,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from jointforces_b200 import _lib
-    from jointforces_b200.simulation import radial_median_curve, lookup_bins
-    from jointforces_b200.sweep import gather_table
+    from jointforces_b200 import sweep as jsweep
+    from jointforces_b200.simulation import lookup_bins, spherical_boundary_conditions
+    from jointforces_b200.mesh import write_msh22
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -237,118 +430,178 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    x_edges, _ = lookup_bins()
-
-    ctx = _lib.Context(case["coords"], case["tets"], case["movable"], n_sys=1, beams=case["beams"], device=local)
-    ctx.set_material(*case["mat"])
-    ctx.set_targets(case["ft"])
-    ctx.set_displacements(np.zeros_like(case["coords"]))
-    info = ctx.info()
-
-    def device_step():
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        ctx.restore_displacements()
-        return ctx.relax(SOLVER["step"], SOLVER["max_iter"], SOLVER["conv_crit"])
-
-    for _ in range(W):
-        device_step()
-    ctx.reset_stats()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    t_wall0 = time.time()
-    for _ in range(K):
-        relrec, cgit, n_iter = device_step()
-    barrier()
-    wall = time.time() - t_wall0
-    clocks = sampler.stop()
-    st = ctx.stats()
-    ms_dev = torch.tensor([st["ms_relax"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_dev, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms_dev.item()) / K
-    value = world * 3600.0 / (ms_per_step * 1e-3)
-
-    # ---- end to end through the host-facing call -----------------------------------------------
-    def e2e_step():
-        out = _lib.solve_boundarycondition(case["coords"], case["tets"], case["movable"], case["ft"],
-                                           np.zeros_like(case["coords"]), case["mat"], SOLVER["step"], SOLVER["max_iter"],
-                                           SOLVER["conv_crit"], beams=case["beams"], device=local)
-        curve = radial_median_curve(case["coords"], out["U"], case["r_in"], x_edges)
-        gather_table([rank], [case["pressure"]], curve[None, :], world, len(curve))
-        return out
-
-    e2e_step()
-    barrier()
-    t0 = time.time()
-    for _ in range(K):
-        flush.fill_(1)
-        out = e2e_step()
-    barrier()
-    e2e_ms = torch.tensor([(time.time() - t0) * 1e3 / K], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * 3600.0 / (float(e2e_ms.item()) * 1e-3)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     peaks, peak_kind = measured_peaks()
-    cg_iters = st["cg_iterations"]
-    by_iter = cg_bytes_per_iteration(info)
-    achieved = by_iter * cg_iters / (st["ms_cg"] * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "cg_traffic_%s.json" % args.workload)
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    matrix_mb = info["n_blocks"] * 72 / 1e6
-    line = {
-        "metric": "lookup-table sims/hour", "value": value, "unit": "sims/hour", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": case["text"], "n_nodes": info["n_nodes"], "n_free": info["n_free"], "n_tets": info["n_tets"],
-                   "nonzero_blocks": info["n_blocks"], "directions": "%d folded to %d" % (info["n_beams"], info["n_dirs"]),
-                   "solver": SOLVER, "newton_steps": int(n_iter[0]), "cg_iterations_per_solve": int(cgit[0].sum()),
-                   "l2": "flushed between steps (256 MB write)", "parallelism": "independent solves, 1 per GPU"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "sims/hour", "h2d_bytes_per_step": int(out["stats"]["bytes_h2d"]),
-                "d2h_bytes_per_step": int(out["stats"]["bytes_d2h"]), "ms_per_step": float(e2e_ms.item())},
-        "gpu_launches": int(st["kernel_launches"]),
-        "submetrics": {
-            "tet_updates_per_s": st["tet_updates"] / (st["ms_element"] * 1e-3),
-            "cg_iters_per_s": cg_iters / (st["ms_cg"] * 1e-3),
-            "ms_element": st["ms_element"] / K, "ms_assembly": st["ms_assembly"] / K, "ms_cg": st["ms_cg"] / K,
-            "wall_ms_per_step": wall * 1e3 / K,
-        },
-        "roofline": {"bound": "hbm", "kernel": "jf_cg_fused_kernel" if info.get("cg_fused") == 1 else "jf_cg_fused_stream_kernel" if info.get("cg_fused") == 2 else
-                     "jf_cg_regres_kernel" if info["cg_resident"] == 2 else
-                     ("jf_cg_resident_kernel" if info["cg_resident"] == 1 else
-                      ("jf_cg_streamhalo_kernel" if info.get("cg_stream_halo") else "jf_cg_stream_kernel")), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": "of " + peak_kind,
-                     "algorithmic_bytes_per_launch": by_iter * cg_iters / max(1, st["cg_launches"]),
-                     "note": ("matrix %.0f MB %s the 126 MB L2; " % (matrix_mb, "fits in" if matrix_mb < 100 else "exceeds")) +
-                             ("it is staged once per CG solve into registers/shared memory, so `achieved` is a rate of "
-                              "algorithmic bytes (latency/barrier-bound regime), not DRAM traffic; `traffic` is the measured "
-                              "DRAM bytes of one launch; see roofline_large for the HBM-bound regime" if info["cg_resident"] else "")},
-    }
+    line = {"metric": "lookup-table sims/hour", "unit": "sims/hour", "n_gpus": world, "steps": K, "warmup": W,
+            "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": shared_config(case, args.workload)}
+
+    if args.workload != "cfg3":
+        sampler = ClockSampler(local)
+        sampler.start()
+        r = single_solve_legs(case, local, K, W, flush, barrier, world, rank, dist, torch)
+        clocks = sampler.stop()
+        if rank != 0:
+            if world > 1:
+                dist.destroy_process_group()
+            return
+        st, info = r["st"], r["info"]
+        line.update(value=world * 3600.0 / (r["ms_per_step"] * 1e-3), ms_per_step=r["ms_per_step"], scaling="weak", clocks=clocks,
+                    e2e={"value": world * 3600.0 / (r["e2e_ms"] * 1e-3), "unit": "sims/hour", "h2d_bytes_per_step": r["h2d"],
+                         "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["e2e_ms"], "steps": r["e2e_steps"]},
+                    gpu_launches=int(st["kernel_launches"]),
+                    submetrics={"tet_updates_per_s": st["tet_updates"] / (st["ms_element"] * 1e-3),
+                                "cg_iters_per_s": st["cg_iterations"] / (st["ms_cg"] * 1e-3), "ms_element": st["ms_element"] / K,
+                                "ms_assembly": st["ms_assembly"] / K, "ms_cg": st["ms_cg"] / K, "wall_ms_per_step": r["wall_ms"],
+                                "newton_steps": r["newton"], "cg_iterations_per_solve": r["cg"]},
+                    roofline=roofline_of(info, st, peaks, peak_kind, args.workload),
+                    notes={"l2": "flushed between steps (256 MB write)", "parallelism": "independent solves, 1 per GPU",
+                           "nonzero_blocks": info["n_blocks"], "directions": "%d folded to %d" % (info["n_beams"], info["n_dirs"])})
+    else:
+        # ---- the sweep: device-timed leg through a resident engine ---------------------------------------------------
+        mat_dict = case["mat_dict"]
+        x_edges, _ = lookup_bins()
+        r_curve = (R_IN * 1e6) * 10 ** -6
+        engine = jsweep.SweepEngine(case["coords"], case["tets"], case["bc"]["displacement"], mat_dict, SOLVER["step"],
+                                    SOLVER["max_iter"], SOLVER["conv_crit"], device=local, curve_bins=(r_curve, x_edges))
+        info = engine.info()
+        costs_all = jsweep.pressure_cost(TABLE, mat_dict)
+
+        def device_step(j):
+            idx = step_indices(j)
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            order = idx[np.argsort(-costs_all[idx], kind="stable")]
+            claimer = jsweep._Claimer(order, costs_all[order], rank, world, "dynamic")
+            ms, rows, done = 0.0, [], []
+            while True:
+                chunk = claimer.take(engine.batch)
+                if not chunk:
+                    break
+                forces = [spherical_boundary_conditions(case["coords"], R_IN, R_OUT, float(TABLE[i]))["forces"] for i in chunk]
+                for i, res in zip(chunk, engine.relax_batch(forces, fetch_fields=False)):
+                    ms += res["ms"]
+                    rows.append(res["curve"])
+                    done.append(i)
+            jsweep.gather_table(done, TABLE[done], np.asarray(rows).reshape(len(done), -1), len(TABLE), len(x_edges) - 1, device=local)
+            t = torch.tensor([ms, -ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)      # (max, -min) of the ranks' device time for this step
+            return float(t[0].item()), -float(t[1].item()), len(done)
+
+        for j in range(W):
+            device_step(j)
+        engine.totals = None
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        t_wall0 = time.time()
+        ms_max = ms_min = 0.0
+        mine = 0
+        for j in range(K):
+            a, b, n_mine = device_step(W + j)
+            ms_max += a
+            ms_min += b
+            mine += n_mine
+        barrier()
+        wall = time.time() - t_wall0
+        clocks = sampler.stop()
+        st = engine.totals or {}
+        engine.close()
+        S = len(step_indices(0))
+        value = K * S * 3600.0 / (ms_max * 1e-3)
+        launches = torch.tensor([float(st.get("kernel_launches", 0))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+
+        # ---- end to end through run_sweep: mesh file in, folders out ----------------------------------------------
+        tmp = tempfile.mkdtemp(prefix="jf_bench_") if rank == 0 else None
+        if world > 1:
+            box = [tmp]
+            dist.broadcast_object_list(box, src=0)
+            tmp = box[0]
+        meshfile = os.path.join(tmp, "mesh.msh")
+        if rank == 0:
+            write_msh22(meshfile, case["coords"], case["tets"], 100, 10000, case["length_factor"])
+        barrier()
+
+        def e2e_step(j):
+            out = os.path.join(tmp, "sweep%d" % j)
+            barrier()
+            t0 = time.time()
+            table = jsweep.run_sweep(meshfile, out, TABLE[step_indices(j)], mat_dict, max_iter=SOLVER["max_iter"], step=SOLVER["step"],
+                                     conv_crit=SOLVER["conv_crit"])
+            barrier()
+            dt = time.time() - t0
+            if rank == 0:
+                shutil.rmtree(out, ignore_errors=True)
+            return dt, table
+
+        e2e_step(0)
+        Ke = min(K, 5)
+        e2e_s, h2d, d2h = 0.0, 0.0, 0.0
+        for j in range(Ke):
+            flush.fill_(1)
+            dt, table = e2e_step(W + j)
+            e2e_s += dt
+            h2d += table["stats"]["bytes_h2d"] if table["stats"] else 0
+            d2h += table["stats"]["bytes_d2h"] if table["stats"] else 0
+        tt = torch.tensor([e2e_s, h2d, d2h], dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx = tt[:1].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            tt[0] = mx[0]
+        e2e_s, h2d, d2h = (float(v) for v in tt.tolist())
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+        line.update(value=value, ms_per_step=ms_max / K, scaling="strong", clocks=clocks,
+                    e2e={"value": Ke * S * 3600.0 / e2e_s, "unit": "sims/hour", "h2d_bytes_per_step": int(h2d / Ke),
+                         "d2h_bytes_per_step": int(d2h / Ke), "ms_per_step": e2e_s * 1e3 / Ke, "steps": Ke,
+                         "path": "run_sweep: msh file -> structure -> H2D -> 30 relaxations -> D2H -> folders written -> gather"},
+                    gpu_launches=int(launches.item()),
+                    submetrics={"tet_updates_per_s": st["tet_updates"] / (st["ms_element"] * 1e-3),
+                                "cg_iters_per_s": st["cg_iterations"] / (st["ms_cg"] * 1e-3),
+                                "rank0_ms_element": st["ms_element"] / K, "rank0_ms_assembly": st["ms_assembly"] / K,
+                                "rank0_ms_cg": st["ms_cg"] / K, "wall_ms_per_step": wall * 1e3 / K,
+                                "rank_busy_spread": (ms_max - ms_min) / ms_max if ms_max > 0 else 0.0,
+                                "solves_on_rank0": mine, "ms_per_solve": ms_max / K / S * world},
+                    roofline=roofline_of(info, st, peaks, peak_kind, args.workload),
+                    notes={"l2": "flushed between steps (256 MB write)", "schedule": "shared work counter (dynamic), most expensive first",
+                           "nonzero_blocks": info["n_blocks"], "directions": "%d folded to %d" % (info["n_beams"], info["n_dirs"])})
+        if world == 1 and not args.no_single:
+            try:
+                c2 = build_case("cfg2")
+                r = single_solve_legs(c2, local, min(K, 5), 3, flush, barrier, world, rank, dist, torch)
+                line["single_solve"] = {"workload": c2["text"], "value": 3600.0 / (r["ms_per_step"] * 1e-3), "ms_per_step": r["ms_per_step"],
+                                        "e2e_value": 3600.0 / (r["e2e_ms"] * 1e-3), "e2e_ms_per_step": r["e2e_ms"],
+                                        "newton_steps": r["newton"], "cg_iterations": r["cg"],
+                                        "us_per_cg_iteration": r["st"]["ms_cg"] * 1e3 / max(1, r["st"]["cg_iterations"]),
+                                        "ms_element": r["st"]["ms_element"] / min(K, 5), "ms_assembly": r["st"]["ms_assembly"] / min(K, 5),
+                                        "ms_cg": r["st"]["ms_cg"] / min(K, 5)}
+            except Exception as e:
+                line["single_solve"] = {"error": str(e)[:200]}
+
     if not args.no_hbm_leg:
         try:
             line["roofline_large"] = hbm_regime_leg(local, peaks)
         except Exception as e:   # never lose the main line to the extra leg
             line["roofline_large"] = {"error": str(e)[:200]}
-    if not args.no_cpu:
-        cores = os.cpu_count() or 1
-        dt, r = cpu_sample(case, args.cpu_newton, cores)
-        full, full_cg = int(n_iter[0]), int(cgit[0].sum())
-        est = cpu_full_solve_estimate(r, dt, full, full_cg)
-        line["cpu_baseline"] = {"value": 3600.0 / est, "unit": "sims/hour", "cores": cores, "kind": "port",
-                                "sample": "first %d of %d Newton iterations of the same solve with oracle/saeno_oracle.c on %d "
-                                          "threads, %.1f s; element part scaled by evaluations, CG part by CG iterations "
-                                          "(%d per solve) -> %.1f s per solve" % (args.cpu_newton, full, cores, dt, full_cg, est)}
+    if not args.no_cpu and world == 1:
+        try:
+            pool = CpuPool(case, args.cpu_procs)
+            try:
+                wall, out = pool.wave(wave_pressures(case, args.workload, W, pool.procs))
+            finally:
+                pool.close()
+            line["cpu_baseline"] = {"value": len(out) * 3600.0 / wall, "unit": "sims/hour", "cores": pool.cores, "kind": out[0][3],
+                                    "sample": "%d complete solves at once (%d processes x %d threads, %s), %.1f s; Newton steps %s, CG "
+                                              "iterations %s" % (len(out), pool.procs, pool.threads, pool.describe(), wall,
+                                                                 [o[1] for o in out], [o[2] for o in out])}
+        except Exception as e:
+            line["cpu_baseline"] = {"error": str(e)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

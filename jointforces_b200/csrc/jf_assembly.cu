@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) jf_gather_f_kernel(const int32_t *__restr
 
 // fixed-order reductions: strain energy, |f - f_t|^2 and |f|^2 over free nodes.  The energy counts only tetrahedra
 // with at least one free node (free nodes are numbered first: some corner < Nf), as saenopy's `_update_energy` does
-// (oracle/saeno_oracle.py `energy_rule`); Et itself keeps every tet's energy for jf_get_element_quantities.  RED_CTAS CTAs per system take
+// (SURVEY Appendix A5); Et itself keeps every tet's energy for jf_get_element_quantities.  RED_CTAS CTAs per system take
 // fixed strided shares and publish partial sums; the CTA that arrives last (self-resetting ticket) adds them in
 // index order -- deterministic whatever the arrival order.
 constexpr int RED_CTAS = 32;

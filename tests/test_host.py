@@ -3,6 +3,7 @@ saenopy object protocol mirror, the C ABI's symbol table, sweep sharding and the
 (gloo, world_size 2).  No compute calls: this box has no GPU."""
 import inspect
 import os
+import time
 import re
 
 import numpy as np
@@ -262,13 +263,58 @@ def test_linear_lookup_interpolator_rescales(tmp_path):
 
 # ---- sweep sharding and the gather ------------------------------------------------------------------------
 def test_shard_indices_partition_and_balance():
+    """Static schedule: longest-processing-time-first on the cost model -- a partition, and balanced in COST (not count)."""
     values = np.logspace(-1, 4, 150)
+    cost = sweep.pressure_cost(values, {"K_0": 1645.0})
+    assert cost.min() >= 1.0 and 1.3 < cost.max() < 3.0 and cost[0] < cost.max() > cost[-1]    # dearest in the middle decades
     for world in (1, 2, 4, 8):
         parts = [sweep.shard_indices(values, r, world) for r in range(world)]
         assert sorted(np.concatenate(parts).tolist()) == list(range(150))
-        top = [values[p].max() for p in parts]
-        assert sorted(top) == sorted(values[-world:])          # the `world` most expensive pressures land on distinct ranks
-        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= cost.max()                      # LPT bound: within one item
+        assert loads.max() / loads.mean() < 1.02
+    # a stiffer material shifts the curve along the pressure axis
+    assert np.argmax(sweep.pressure_cost(values, {"K_0": 5208.0})) > np.argmax(cost)
+
+
+def _queue_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    taken = []
+    for sweep_no in range(2):                                   # two sweeps: each gets its own counter
+        values = np.logspace(-1, 4, 23)
+        cost = sweep.pressure_cost(values)
+        order = np.argsort(-cost, kind="stable")
+        claimer = sweep._Claimer(order, cost, rank, world, "dynamic")
+        assert claimer.store is not None
+        mine = []
+        while True:
+            chunk = claimer.take(2 if rank else 1)              # ranks may draw different chunk sizes
+            if not chunk:
+                break
+            mine += chunk
+            time.sleep(0.002 * (1 + rank))                      # uneven speeds: the faster rank ends up with more
+        taken.append(mine)
+        dist.barrier()
+    np.savez(os.path.join(out_dir, "q%d.npz" % rank), a=np.array(taken[0]), b=np.array(taken[1]))
+    dist.destroy_process_group()
+
+
+def test_dynamic_work_queue_two_ranks_gloo(tmp_path):
+    """The shared counter in the process group's store hands every load case to exactly one rank, most expensive first."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_queue_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    q = [np.load(tmp_path / ("q%d.npz" % r)) for r in range(2)]
+    for key in ("a", "b"):
+        both = np.concatenate([q[0][key], q[1][key]])
+        assert sorted(both.tolist()) == list(range(23))
+        assert len(q[0][key]) > 0 and len(q[1][key]) > 0
+    cost = sweep.pressure_cost(np.logspace(-1, 4, 23))
+    first = [int(q[r]["a"][0]) for r in range(2)]
+    assert set(first) <= set(np.argsort(-cost, kind="stable")[:3].tolist())   # the dearest cases go out first
 
 
 def _gloo_worker(rank, world, port, out_dir):

@@ -85,26 +85,44 @@ def test_spherical_contraction_solver_hands_over_what_the_reference_does(g, tmp_
     assert "Inner node spacing: " in out and "Outer node spacing: " in out
 
 
-def fake_relax_load_cases(golden):
-    """Stands in for the device: returns the displacement fields the generator's recorder wrote."""
-    def run(coords, tets, bc_displacement, forces_list, material, step, max_iter, conv_crit, device=0, batch=None, curve_bins=None,
-            fetch_fields=True, warm_start=False):
-        assert same(coords, golden["sweep_nodes"]) and max_iter == 77 and (step, conv_crit) == (0.0033, 0.01)
-        r_curve, x = curve_bins
-        res = []
-        for i in range(len(forces_list)):
-            U = golden["sweep_displacements"][i]
-            res.append({"U": U, "forces": np.zeros_like(U), "relrec": np.zeros((2, 3)),
-                        "curve": sim.radial_median_curve(coords, U, r_curve, x)})
-        return res, None
-    return run
+def fake_engine(golden):
+    """Stands in for the device (sweep.SweepEngine): returns the displacement fields the generator's recorder wrote,
+    recognising the load case by its total inner-shell force."""
+    forces_of = {}
+
+    class Engine:
+        batch = 1
+        totals = None
+
+        def __init__(self, coords, tets, bc_displacement, material, step, max_iter, conv_crit, device=0, batch=None, beams=None,
+                     curve_bins=None, initial_displacements=None):
+            assert same(coords, golden["sweep_nodes"]) and max_iter == 77 and (step, conv_crit) == (0.0033, 0.01)
+            self.coords, (self.r_curve, self.x) = coords, curve_bins
+            for i, v in enumerate(np.logspace(-1, 4, 7)):
+                f = sim.spherical_boundary_conditions(coords, 100e-6, 10000e-6, float(v))["forces"]
+                forces_of[float(np.nansum(np.abs(f)))] = i
+
+        def relax_batch(self, forces_list, fetch_fields=True, keep_displacements=False):
+            out = []
+            for f in forces_list:
+                key = float(np.nansum(np.abs(f)))
+                i = forces_of[min(forces_of, key=lambda k: abs(k - key))]
+                U = golden["sweep_displacements"][i]
+                out.append({"U": U, "forces": np.zeros_like(U), "relrec": np.zeros((2, 3)), "cg_iters": np.zeros(1, int), "ms": 1.0,
+                            "curve": sim.radial_median_curve(self.coords, U, self.r_curve, self.x)})
+            return out
+
+        def close(self):
+            pass
+    return Engine
+
 
 
 def test_distribute_solver_files_and_table_match_reference(g, tmp_path, monkeypatch):
     """distribute_solver -> folders -> create_lookup_table_solver, with the device replaced by the golden fields:
     values file, folder names, every parameters.txt, callbacks and the table equal the reference's."""
     (tmp_path / "mid.msh").write_text(str(g["sweep_msh"]))
-    monkeypatch.setattr(sweep, "relax_load_cases", fake_relax_load_cases(g))
+    monkeypatch.setattr(sweep, "SweepEngine", fake_engine(g))
     seen = []
     const_args = {"meshfile": str(tmp_path / "mid.msh"), "outfolder": str(tmp_path / "sweep"), "material": jf.materials.collagen12,
                   "max_iter": 77}
@@ -114,7 +132,9 @@ def test_distribute_solver_files_and_table_match_reference(g, tmp_path, monkeypa
     assert open(tmp_path / "sweep" / "pressure-values.txt").read() == str(g["sweep_values_txt"])
     assert sorted(os.listdir(tmp_path / "sweep")) == list(g["sweep_listing"])
     # the reference calls back after every solve and once more at the end (:246-247) with (n, n)
-    assert [tuple(s) for s in seen] == [tuple(s) for s in g["sweep_callbacks"]][:len(seen)] and len(seen) >= 7
+    # the reference calls back (index, n) after every launch in index order (and once more with (n, n)); here the
+    # solves finish most-expensive-first, so the same calls arrive in schedule order
+    assert sorted(tuple(s) for s in seen) == sorted(tuple(s) for s in g["sweep_callbacks"])[:len(seen)] and len(seen) >= 7
     for i in range(7):
         folder = tmp_path / "sweep" / ("simulation%06d" % i)
         assert open(folder / "parameters.txt", encoding="utf-8").read() == str(g["sweep_parameters"][i])
@@ -123,8 +143,19 @@ def test_distribute_solver_files_and_table_match_reference(g, tmp_path, monkeypa
     assert same(table["pressure"], g["table_pressure"]) and same(table["x"], g["table_x"]) and same(table["y"], g["table_y"])
     assert 10 < (~np.isnan(table["y"][0])).sum() < 100            # populated and empty bins both occur
     # linear spacing branch (the reference spaces the logarithms, :192)
-    monkeypatch.setattr(sweep, "relax_load_cases", lambda *a, **k: ([{"U": np.zeros((72, 3)), "forces": np.zeros((72, 3)),
-                                                                      "relrec": np.zeros((1, 3)), "curve": np.full(100, np.nan)}] * 3, None))
+    class Zero:
+        batch, totals = 1, None
+
+        def __init__(self, *a, **k):
+            pass
+
+        def relax_batch(self, forces_list, fetch_fields=True, keep_displacements=False):
+            return [{"U": np.zeros((72, 3)), "forces": np.zeros((72, 3)), "relrec": np.zeros((1, 3)), "cg_iters": np.zeros(0, int),
+                     "ms": 0.0, "curve": np.full(100, np.nan)} for _ in forces_list]
+
+        def close(self):
+            pass
+    monkeypatch.setattr(sweep, "SweepEngine", Zero)
     (tmp_path / "small.msh").write_text(str(g["small_msh"]))
     sim.distribute_solver("ignored", {"meshfile": str(tmp_path / "small.msh"), "outfolder": str(tmp_path / "lin"),
                                       "material": jf.materials.collagen12}, start=1, end=100, n=3, log_scaling=False, n_cores=1)
