@@ -407,6 +407,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # the library mirrors the reference's prints (mesh geometry notices ...): keep stdout for the one JSON line
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
 
     import torch
     import torch.distributed as dist
@@ -602,7 +605,8 @@ def main():
                                                                  [o[1] for o in out], [o[2] for o in out])}
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)[:200]}
-    print(json.dumps(line))
+    print(json.dumps(line), file=real_stdout)
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
