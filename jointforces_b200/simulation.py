@@ -191,6 +191,8 @@ def spherical_contraction_solver(meshfile, outfolder, pressure, material, r_inne
     M.solve_boundarycondition(step_size=step, max_iterations=max_iter, rel_conv_crit=conv_crit,
                               relrecname=outfolder + "/relrec.txt")
     M.save(outfolder + "/solver.saenopy")
+    # the legacy archive the reference's last loader fallback reads with any saenopy version (:252-258, 289-291)
+    M.save(outfolder + "/solver.npz", layout="legacy")
     return M
 
 

@@ -51,7 +51,8 @@ class SemiAffineFiberMaterial:
         return self.k, self.d0, self.lambda_s, self.ds
 
     def serialize(self):
-        return dict(type="SemiAffineFiberMaterial", k=self.k, d_0=self.d0, lambda_s=self.lambda_s, d_s=self.ds)
+        """saenopy's form: ``['SemiAffineFiberMaterial', k, d_0, lambda_s, d_s]``."""
+        return ["SemiAffineFiberMaterial", self.k, self.d0, self.lambda_s, self.ds]
 
     def __repr__(self):
         return "SemiAffineFiberMaterial(k=%r, d0=%r, lambda_s=%r, ds=%r)" % self.as_tuple()
@@ -179,9 +180,9 @@ class Solver:
         return self.relrec
 
     # ---- persistence (simulation.py:168, 278-291) -------------------------------------------------------
-    def save(self, filename):
+    def save(self, filename, layout="saenopy"):
         save_solver_file(filename, self.mesh.nodes, self.mesh.tetrahedra, self.mesh.displacements, self.mesh.forces,
-                         self.mesh.forces_target, self.mesh.movable, self.material_parameters, self.relrec)
+                         self.mesh.forces_target, self.mesh.movable, self.material_parameters, self.relrec, layout=layout)
 
     # legacy attribute names (simulation.py:213, 286-287)
     @property
@@ -214,20 +215,44 @@ class Solver:
         return float(-np.sum(np.einsum("ij,ij->i", f, d) / dist))
 
 
-def save_solver_file(filename, nodes, tets, displacements, forces, forces_target, movable, material_parameters, relrec):
-    """Write an npz archive under ``filename`` (for ``solver.saenopy``: no extra suffix), with flat
-    ``group/field`` keys like saenopy's ``Saveable`` and the legacy keys R, T, U, f that
-    ``simulation.py:254-258`` reads."""
-    data = {
-        "mesh/nodes": nodes, "mesh/tetrahedra": tets, "mesh/displacements": displacements, "mesh/forces": forces,
-        "mesh/forces_target": forces_target, "mesh/movable": movable,
-        "R": nodes, "T": tets, "U": displacements, "f": forces,
-    }
-    if material_parameters:
-        for k, v in material_parameters.items():
-            data["material_parameters/" + k] = np.asarray(v)
-    if relrec is not None:
-        data["relrec"] = np.asarray(relrec)
+def _material_list(material_parameters):
+    """saenopy's ``material.serialize()``: ``['SemiAffineFiberMaterial', k, d_0, lambda_s, d_s]`` (rebuilt on load with
+    ``SemiAffineFiberMaterial(*material_parameters[1:])``)."""
+    if material_parameters is None:
+        return None
+    if isinstance(material_parameters, dict):
+        m = material_parameters
+        return [m.get("type", "SemiAffineFiberMaterial"), m["k"], m["d_0"], m["lambda_s"], m["d_s"]]
+    return list(material_parameters)
+
+
+def save_solver_file(filename, nodes, tets, displacements, forces, forces_target, movable, material_parameters, relrec,
+                     layout="saenopy"):
+    """Write an npz archive under ``filename`` (for ``solver.saenopy``: no extra suffix).
+
+    ``layout='saenopy'`` (default) follows saenopy's ``Saveable`` as recalled (the package is absent here, DESIGN.md
+    "Known gaps"): nested fields flattened to ``group/field`` keys, a list stored as the marker string ``"list"`` under
+    its own key plus ``key/0 .. key/n``, and NO key saenopy's ``Solver`` / ``SolverMesh`` constructors do not take --
+    ``mesh/{nodes, tetrahedra, displacements, forces, forces_target, movable}``, ``material_parameters`` (+``/0../4``)
+    and ``relrec``.  ``layout='legacy'`` writes the pre-1.0 keys ``R, T, U, f`` (plus ``f_target, var``) that
+    ``simulation.py:254-258`` reads through its last fallback.  ``load_solver`` below reads both."""
+    nodes, displacements = np.asarray(nodes), np.asarray(displacements)
+    if layout == "legacy":
+        data = {"R": nodes, "T": np.asarray(tets), "U": displacements, "f": np.asarray(forces),
+                "f_target": np.asarray(forces_target), "var": np.asarray(movable)}
+    elif layout == "saenopy":
+        data = {"mesh/nodes": nodes, "mesh/tetrahedra": np.asarray(tets), "mesh/displacements": displacements,
+                "mesh/forces": np.asarray(forces), "mesh/forces_target": np.asarray(forces_target),
+                "mesh/movable": np.asarray(movable)}
+        mat = _material_list(material_parameters)
+        if mat is not None:
+            data["material_parameters"] = np.asarray("list")
+            for i, v in enumerate(mat):
+                data["material_parameters/%d" % i] = np.asarray(v)
+        if relrec is not None:
+            data["relrec"] = np.asarray(relrec)
+    else:
+        raise ValueError("layout must be 'saenopy' or 'legacy'")
     tmp = str(filename) + ".tmp.npz"
     np.savez(tmp, **data)
     shutil.move(tmp, str(filename))
@@ -260,10 +285,14 @@ def load_solver(filename):
         s.mesh.forces_target = get("mesh/forces_target", "f_target")
         s.mesh.movable = get("mesh/movable", "var")
         mp = {k.split("/", 1)[1]: z[k][()] for k in keys if k.startswith("material_parameters/")}
+        if mp and all(k.isdigit() for k in mp):          # saenopy's list layout: [type, k, d_0, lambda_s, d_s]
+            vals = [mp[str(i)] for i in range(len(mp))]
+            mp = dict(type=str(vals[0]), k=float(vals[1]), d_0=float(vals[2]), lambda_s=float(vals[3]), d_s=float(vals[4]))
         if mp:
-            s.material_parameters = {k: (str(v) if k == "type" else float(v)) for k, v in mp.items()}
-            s.material_model = SemiAffineFiberMaterial(s.material_parameters["k"], s.material_parameters["d_0"],
-                                                       s.material_parameters["lambda_s"], s.material_parameters["d_s"])
+            none_to_big = lambda v: 1e30 if v is None or (isinstance(v, float) and np.isnan(v)) else float(v)
+            s.material_model = SemiAffineFiberMaterial(none_to_big(mp["k"]), none_to_big(mp["d_0"]), none_to_big(mp["lambda_s"]),
+                                                       none_to_big(mp["d_s"]))
+            s.material_parameters = s.material_model.serialize()
     if s.mesh.nodes is None or s.mesh.displacements is None:
         raise ValueError("%s holds neither mesh/nodes nor R" % filename)
     return s

@@ -212,7 +212,7 @@ def relax_load_cases(coords, tets, bc_displacement, bc_forces_list, material, st
     return results, totals
 
 
-def _write_case(folder, coords, tets, material, mat_par, value, bc, r_in, r_out, res):
+def _write_case(folder, coords, tets, material, mat_par, value, bc, r_in, r_out, res, legacy_npz=True):
     from . import simulation as sim
     from .solver import save_solver_file
     os.makedirs(folder, exist_ok=True)
@@ -221,14 +221,19 @@ def _write_case(folder, coords, tets, material, mat_par, value, bc, r_in, r_out,
     movable = np.any(np.isnan(bc['displacement']), axis=1)
     save_solver_file(folder + "/solver.saenopy", coords, tets, res['U'], res['forces'], np.nan_to_num(bc['forces']), movable,
                      mat_par, res['relrec'])
+    if legacy_npz:   # what the reference's last loader fallback reads (simulation.py:252-258, 289-291) whatever saenopy it runs on
+        save_solver_file(folder + "/solver.npz", coords, tets, res['U'], res['forces'], np.nan_to_num(bc['forces']), movable,
+                         mat_par, res['relrec'], layout="legacy")
 
 
 def run_sweep(meshfile, outfolder, values, material, var_arg='pressure', max_iter=600, step=0.0033, conv_crit=0.01,
               batch=None, callback=None, r_inner=None, r_outer=None, x0=1, x1=50, n_bins=100, write=True,
-              warm_start=False, schedule="dynamic", engine=None):
+              warm_start=False, schedule="dynamic", engine=None, legacy_npz=True):
     """Solve ``values`` (pressures), write the reference's folder layout and return the lookup table
     ``{'pressure','x','y'}`` (complete on every rank when ``torch.distributed`` is initialised, else this
-    rank's rows).  ``schedule``: 'dynamic' (shared work counter, needs a process group; falls back to 'lpt'
+    rank's rows).  Every folder also gets a legacy ``solver.npz`` (keys R, T, U, f; ``legacy_npz=False`` skips it): the
+    reference's table builder falls back to it when the saenopy it runs on cannot read our ``solver.saenopy``
+    (simulation.py:278-291).  ``schedule``: 'dynamic' (shared work counter, needs a process group; falls back to 'lpt'
     without one) or 'lpt' (static, by ``pressure_cost``).  ``warm_start`` implies a static ascending order on one
     rank's share.  ``engine``: a live ``SweepEngine`` for this mesh/material to reuse (its context stays resident)."""
     from . import simulation as sim
@@ -279,7 +284,7 @@ def run_sweep(meshfile, outfolder, values, material, var_arg='pressure', max_ite
                 if write:
                     folder = outfolder + '/simulation' + str(int(i)).zfill(6)
                     pending.append(writer.submit(_write_case, folder, coords, tets64, material, mat_par, float(values[i]), bc,
-                                                 r_in, r_out, res))
+                                                 r_in, r_out, res, legacy_npz))
                 if callback is not None:
                     callback(int(i), len(values))
         for p in pending:

@@ -22,7 +22,7 @@ def test_spherical_contraction_solver_writes_reference_files(meshfile, tmp_path,
     from oracle import c_oracle
     out = str(tmp_path / "single")
     M = jf.simulation.spherical_contraction_solver(meshfile, out, 100.0, jf.materials.collagen12)
-    assert sorted(os.listdir(out)) == ["parameters.txt", "relrec.txt", "solver.saenopy"]
+    assert sorted(os.listdir(out)) == ["parameters.txt", "relrec.txt", "solver.npz", "solver.saenopy"]
     par = jf.simulation.read_parameters(out)
     assert par["PRESSURE"] == 100.0 and abs(par["INNER_RADIUS"] - 100.0) < 1e-9 and par["TOTAL_NODES"] == 360
     relrec = np.loadtxt(out + "/relrec.txt")

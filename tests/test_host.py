@@ -196,8 +196,21 @@ def test_solver_protocol_host_side(tmp_path):
     assert np.array_equal(L.mesh.nodes, nodes) and np.array_equal(L.mesh.displacements, M.mesh.displacements)
     assert np.array_equal(L.R, nodes) and np.array_equal(L.U, M.mesh.displacements) and np.array_equal(L.f, M.mesh.forces)
     assert L.material_model.as_tuple() == (1645.0, 0.0008, 0.0075, 0.033)
+    # saenopy's Saveable layout as recalled: group/field keys, the material as a flattened list, and no key its
+    # constructors would not take (extra keys make Solver(**data) raise)
     z = np.load(str(tmp_path / "solver.saenopy"))
-    assert {"R", "U", "f", "mesh/nodes", "mesh/displacements", "mesh/forces"} <= set(z.files)
+    assert set(z.files) == {"mesh/nodes", "mesh/tetrahedra", "mesh/displacements", "mesh/forces", "mesh/forces_target", "mesh/movable",
+                            "material_parameters", "material_parameters/0", "material_parameters/1", "material_parameters/2",
+                            "material_parameters/3", "material_parameters/4", "relrec"}
+    assert str(z["material_parameters"]) == "list" and str(z["material_parameters/0"]) == "SemiAffineFiberMaterial"
+    assert [float(z["material_parameters/%d" % i]) for i in range(1, 5)] == [1645.0, 0.0008, 0.0075, 0.033]
+    assert M.material_parameters == ["SemiAffineFiberMaterial", 1645.0, 0.0008, 0.0075, 0.033] == L.material_parameters
+    # the legacy archive the reference's last loader fallback reads (simulation.py:252-258): np.load keys R, U, f
+    M.save(str(tmp_path / "solver.npz"), layout="legacy")
+    z = np.load(str(tmp_path / "solver.npz"), allow_pickle=True)
+    assert np.array_equal(z["R"], nodes) and np.array_equal(z["U"], M.mesh.displacements) and np.array_equal(z["f"], M.mesh.forces)
+    L2 = slv.load_solver(str(tmp_path / "solver.npz"))
+    assert np.array_equal(L2.R, nodes) and np.array_equal(L2.mesh.displacements, M.mesh.displacements)
     with pytest.raises(FileNotFoundError):
         slv.load_solver(str(tmp_path / "nope.saenopy"))
 

@@ -138,7 +138,7 @@ def test_distribute_solver_files_and_table_match_reference(g, tmp_path, monkeypa
     for i in range(7):
         folder = tmp_path / "sweep" / ("simulation%06d" % i)
         assert open(folder / "parameters.txt", encoding="utf-8").read() == str(g["sweep_parameters"][i])
-        assert sorted(os.listdir(folder)) == ["parameters.txt", "relrec.txt", "solver.saenopy"]
+        assert sorted(os.listdir(folder)) == ["parameters.txt", "relrec.txt", "solver.npz", "solver.saenopy"]
     table = sim.create_lookup_table_solver(str(tmp_path / "sweep"), 1, 50, 100)
     assert same(table["pressure"], g["table_pressure"]) and same(table["x"], g["table_x"]) and same(table["y"], g["table_y"])
     assert 10 < (~np.isnan(table["y"][0])).sum() < 100            # populated and empty bins both occur
