@@ -109,6 +109,15 @@ int jf_relax(jf_ctx *ctx, double step, int max_iter, double conv_crit, double cg
              int32_t *cg_iters, int32_t *n_iter);
 
 /*
+ * Progress of a jf_relax that is running in another host thread: rows of the relaxation record (du, energy,
+ * residual^2) the device has logged so far for system `sys` (up to max_rows are copied; rows may be NULL to ask for the
+ * count only).  Makes no CUDA call.  Replaces what saenopy does inside solve_boundarycondition after every Newton
+ * step -- np.savetxt(relrecname, relrec) and callback(...) (jointforces/simulation.py:167 passes relrecname) -- the
+ * caller polls this and does both on the host while the GPU runs ahead.
+ */
+int jf_relax_progress(jf_ctx *ctx, int sys, int32_t *n_rows, double *rows, int max_rows);
+
+/*
  * Radial displacement curves on the device -- what extract_deformation_curve_solver computes on the host
  * (simulation.py:296-299): per bin the median of |u|/r_inner over the nodes listed for that bin.
  * The caller classifies the nodes once per mesh: bin_ptr (n_bins+1), bin_nodes (bin_ptr[n_bins]) in the caller's

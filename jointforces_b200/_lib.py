@@ -24,7 +24,7 @@ SYMBOLS = [
     "jf_last_error", "jf_version", "jf_device_count", "jf_ctx_create", "jf_ctx_destroy", "jf_set_material",
     "jf_set_targets", "jf_set_displacements", "jf_get_displacements", "jf_restore_displacements", "jf_get_forces", "jf_evaluate", "jf_get_energy",
     "jf_get_element_quantities", "jf_get_stiffness_blocks", "jf_cg", "jf_get_cg_solution", "jf_relax", "jf_get_stats",
-    "jf_reset_stats", "jf_get_info", "jf_solve_boundarycondition", "jf_bench_fp64", "jf_set_curve_bins", "jf_get_curves", "jf_apply_stiffness",
+    "jf_reset_stats", "jf_get_info", "jf_relax_progress", "jf_solve_boundarycondition", "jf_bench_fp64", "jf_set_curve_bins", "jf_get_curves", "jf_apply_stiffness",
     "jf_msh_open", "jf_msh_read", "jf_msh_close",
     "jf_table_create", "jf_table_destroy", "jf_table_eval", "jf_infer_pressure", "jf_reconstruct_frames", "jf_table_launches",
 ]
@@ -92,6 +92,7 @@ def load():
     L.jf_cg.argtypes = [_vp, C.c_double, C.c_int64, _ip]
     L.jf_get_cg_solution.argtypes = [_vp, C.c_int, _dp]
     L.jf_relax.argtypes = [_vp, C.c_double, C.c_int, C.c_double, C.c_double, _dp, _vp, _ip]
+    L.jf_relax_progress.argtypes = [_vp, C.c_int, C.POINTER(C.c_int32), _vp, C.c_int]
     L.jf_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     L.jf_reset_stats.argtypes = [_vp]
     L.jf_get_info.argtypes = [_vp, C.POINTER(Info)]
@@ -267,11 +268,46 @@ class Context:
         check(self._L.jf_get_cg_solution(self._h, int(sys), out))
         return out
 
-    def relax(self, step, max_iter, conv_crit, cg_tol=0.0):
+    def relax(self, step, max_iter, conv_crit, cg_tol=0.0, on_progress=None, poll_s=0.002):
+        """Relax all systems.  ``on_progress(sys, rows)`` -- ``rows`` the (n, 3) relaxation record logged so far -- is
+        called from THIS thread whenever the device has logged new rows (jf_relax runs in a helper thread meanwhile and
+        keeps enqueueing Newton steps; ctypes releases the GIL), and once more with the complete record at the end."""
         relrec = np.zeros((self.n_sys, max_iter + 1, 3))
         cgit = np.zeros((self.n_sys, max(max_iter, 1)), np.int32)
         n_iter = np.zeros(self.n_sys, np.int32)
-        check(self._L.jf_relax(self._h, float(step), int(max_iter), float(conv_crit), float(cg_tol), relrec, _ptr(cgit), n_iter))
+        call = lambda: self._L.jf_relax(self._h, float(step), int(max_iter), float(conv_crit), float(cg_tol), relrec, _ptr(cgit), n_iter)
+        if on_progress is None:
+            check(call())
+        else:
+            import threading
+            import time
+            box = {}
+
+            def work():
+                try:
+                    box["rc"] = call()
+                    box["err"] = self._L.jf_last_error().decode("utf-8", "replace")   # thread-local in the library
+                except BaseException as e:      # noqa: BLE001 -- re-raised in the caller's thread
+                    box["exc"] = e
+            th = threading.Thread(target=work, daemon=True)
+            seen = [0] * self.n_sys
+            buf = np.zeros((max_iter + 1, 3))
+            n = C.c_int32()
+            th.start()
+            while th.is_alive():
+                th.join(poll_s)
+                for s_ in range(self.n_sys):
+                    if self._L.jf_relax_progress(self._h, s_, C.byref(n), _ptr(buf), max_iter + 1) == 0 and n.value > seen[s_] \
+                            and th.is_alive():
+                        seen[s_] = n.value
+                        on_progress(s_, buf[: n.value].copy())
+            if "exc" in box:
+                raise box["exc"]
+            if box["rc"] < 0:
+                raise JFError("jf_b200 error %d: %s" % (box["rc"], box.get("err", "")))
+            for s_ in range(self.n_sys):
+                if n_iter[s_] + 1 > seen[s_]:
+                    on_progress(s_, relrec[s_, : n_iter[s_] + 1].copy())
         return ([relrec[s, : n_iter[s] + 1].copy() for s in range(self.n_sys)],
                 [cgit[s, : n_iter[s]].copy() for s in range(self.n_sys)], n_iter)
 

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <chrono>
 
 #include "jf_internal.h"
@@ -62,15 +63,57 @@ static double now_ms() {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
+// mapped pinned blocks for the relaxation progress (record rows written by the device, read by the host without a
+// CUDA call).  cudaHostAlloc costs up to ~90 ms, so freed blocks are kept for the next context of the process.
+// ------------------------------------------------------------------------------------------------
+#include <mutex>
+static std::mutex g_pin_mutex;
+static std::vector<std::pair<void *, size_t>> g_pin_free;
+
+static void *pinned_take(size_t bytes, size_t *got) {
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        for (size_t i = 0; i < g_pin_free.size(); i++)
+            if (g_pin_free[i].second >= bytes) {
+                void *p = g_pin_free[i].first;
+                *got = g_pin_free[i].second;
+                g_pin_free.erase(g_pin_free.begin() + i);
+                return p;
+            }
+    }
+    size_t cap = 1 << 16;
+    while (cap < bytes) cap <<= 1;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    *got = cap;
+    return p;
+}
+
+static void pinned_give(void *p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    g_pin_free.emplace_back(p, bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------------
 static void ctx_free(jf_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    pinned_give(c->h_progress, c->h_progress_bytes);
+    c->h_progress = nullptr;
+    for (auto &e : c->ev_ring)
+        if (e) cudaEventDestroy(e);
     void *ptrs[] = {c->d_tets, c->d_nodes, c->d_phi, c->d_vol, c->d_dirtab, c->d_mat, c->d_state, c->d_U, c->d_ft, c->d_f,
                     c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_halo_ptr, c->d_halo_nodes, c->d_lcol, c->d_bin_ptr, c->d_bin_nodes, c->d_curve_scratch,
-                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_r1, c->d_Ap1, c->d_partial, c->d_sync, c->d_red_partial, c->d_red_ticket};
+                    c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_r1, c->d_Ap1, c->d_partial, c->d_sync, c->d_red_partial, c->d_red_ticket,
+                    c->d_relrec};
     if (c->stream) {
         for (void *p : ptrs)
             if (p) cudaFreeAsync(p, c->stream);
@@ -123,6 +166,9 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if (!coop) { jf_set_error("device lacks cooperative launch"); rc = JF_ERR_CUDA; break; }
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "stream", __FILE__, __LINE__); break; }
         for (auto &e : c->ev)
+            if (cudaEventCreate(&e) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
+        if (rc) break;
+        for (auto &e : c->ev_ring)
             if (cudaEventCreate(&e) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
         if (rc) break;
         {   // keep freed workspace in the pool for the next context
@@ -463,6 +509,44 @@ extern "C" int jf_get_cg_solution(jf_ctx *c, int sys, double *uu) {
     return JF_OK;
 }
 
+// Room for the record rows of a relaxation of `max_iter` Newton steps: device rows + a mapped pinned mirror with the
+// per-system progress flags behind it.
+static int relax_log_prepare(jf_ctx *c, int max_iter, double conv_crit) {
+    const int S = c->n_sys, cap = max_iter + 1;
+    if (cap > c->rlog.cap || !c->d_relrec) {
+        if (c->d_relrec) JF_CUDA(cudaFreeAsync(c->d_relrec, c->stream));
+        c->d_relrec = nullptr;
+        int rc = jf_dev_alloc(c, &c->d_relrec, (size_t)S * cap * 4);
+        if (rc) return rc;
+        c->rlog.cap = cap;
+    }
+    const size_t need = (size_t)S * c->rlog.cap * 4 * sizeof(double) + (size_t)S * 2 * sizeof(int);
+    if (need > c->h_progress_bytes) {
+        pinned_give(c->h_progress, c->h_progress_bytes);
+        c->h_progress = pinned_take(need, &c->h_progress_bytes);
+        if (!c->h_progress) { c->h_progress_bytes = 0; jf_set_error("cannot allocate the pinned progress block"); return JF_ERR_NOMEM; }
+    }
+    memset(c->h_progress, 0, need);
+    void *dev = nullptr;
+    JF_CUDA(cudaHostGetDevicePointer(&dev, c->h_progress, 0));
+    c->rlog.rows = c->d_relrec;
+    c->rlog.host_rows = (double *)dev;
+    c->rlog.host_flags = (int *)((char *)dev + (size_t)S * c->rlog.cap * 4 * sizeof(double));
+    c->rlog.max_iter = max_iter;
+    c->rlog.conv_crit = conv_crit;
+    return 0;
+}
+
+static inline const double *progress_rows(const jf_ctx *c, int sys) { return (const double *)c->h_progress + (size_t)sys * c->rlog.cap * 4; }
+static inline const volatile int *progress_flags(const jf_ctx *c) {
+    return (const volatile int *)((const char *)c->h_progress + (size_t)c->n_sys * c->rlog.cap * 4 * sizeof(double));
+}
+
+// The relaxation (A12, A14).  The driver's bookkeeping runs on the device (jf_reduce_kernel: record row, five-energy stop
+// rule, `active` flag that every kernel honours), so the host enqueues RELAX_AHEAD Newton steps at a time and only then
+// looks at the progress the device wrote into mapped memory -- steps enqueued past a system's stop are no-ops.
+constexpr int RELAX_AHEAD = 4;
+
 extern "C" int jf_relax(jf_ctx *c, double step, int max_iter, double conv_crit, double cg_tol, double *relrec, int32_t *cg_iters,
                         int32_t *n_iter) {
     CHECK_CTX(c);
@@ -473,70 +557,94 @@ extern "C" int jf_relax(jf_ctx *c, double step, int max_iter, double conv_crit, 
     const int S = c->n_sys;
     const int64_t cg_maxiter = 3 * c->N;
     const size_t stride = (size_t)(max_iter + 1) * 3;
-    // all systems start active
-    for (int s = 0; s < S; s++) c->h_state[s].active = 1;
+    if ((rc = relax_log_prepare(c, max_iter, conv_crit))) return rc;
+    // all systems start active, no rows logged
+    for (int s = 0; s < S; s++) {
+        c->h_state[s].active = 1;
+        c->h_state[s].n_rows = 0;
+    }
     JF_CUDA(cudaEventRecord(c->ev[5], c->stream));
     JF_CUDA(cudaMemcpyAsync(c->d_state, c->h_state, S * sizeof(jf_sys_state), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = evaluate_async(c, true))) return rc;
-    if ((rc = fetch_state(c))) return rc;
+    c->rlog.enabled = 1;
+    struct Off { jf_ctx *c; ~Off() { c->rlog.enabled = 0; } } off{c};   // plain jf_evaluate calls do not log
+    if ((rc = evaluate_async(c, true))) return rc;                      // row 0 (a system with max_iter == 0 stops here)
+    JF_CUDA(cudaEventSynchronize(c->ev[2]));
     if ((rc = account_eval(c, S))) return rc;
     c->evaluated = true;
-    for (int s = 0; s < S; s++) {
-        double *row = relrec + s * stride;
-        row[0] = 0.0;
-        row[1] = c->h_state[s].energy;
-        row[2] = c->h_state[s].force2;  // saenopy logs sum f^2 (not f - f_target) for the start row
-        n_iter[s] = 0;
-    }
-    int n_active = S;
-    for (int i = 0; i < max_iter && n_active > 0; i++) {
-        JF_CUDA(cudaEventRecord(c->ev[3], c->stream));
-        if ((rc = jf_launch_cg(c, cg_tol, cg_maxiter, step, 1))) return rc;
-        JF_CUDA(cudaEventRecord(c->ev[4], c->stream));
-        if ((rc = evaluate_async(c, true))) return rc;
-        if ((rc = fetch_state(c))) return rc;
-        float ms = 0;
-        JF_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]));
-        c->stats.ms_cg += ms;
-        if ((rc = account_eval(c, n_active))) return rc;
-        bool changed = false;
-        for (int s = 0; s < S; s++) {
-            if (!c->h_state[s].active) continue;
-            double *row = relrec + s * stride + 3 * (size_t)(i + 1);
-            row[0] = c->h_state[s].du;
-            row[1] = c->h_state[s].energy;
-            row[2] = c->h_state[s].residual2;
-            if (cg_iters) cg_iters[(size_t)s * max_iter + i] = c->h_state[s].cg_iters;
-            c->stats.cg_iterations += c->h_state[s].cg_iters;
-            c->stats.newton_steps++;
-            n_iter[s] = i + 1;
-            if (i > 6) {  // five-energy stop rule (A14)
-                double mean = 0.0, var = 0.0;
-                for (int j = 0; j < 5; j++) mean += relrec[s * stride + 3 * (size_t)(i + 1 - j) + 1];
-                mean /= 5.0;
-                for (int j = 0; j < 5; j++) {
-                    double d = relrec[s * stride + 3 * (size_t)(i + 1 - j) + 1] - mean;
-                    var += d * d;
-                }
-                double estd = sqrt(var / 5.0) / sqrt(5.0);
-                if (estd / mean < conv_crit) {
-                    c->h_state[s].active = 0;
-                    changed = true;
-                    n_active--;
-                }
-            }
+    const volatile int *flags = progress_flags(c);
+    int steps = 0;
+    auto n_active = [&]() { int n = 0; for (int s = 0; s < S; s++) n += flags[2 * s + 1] ? 1 : 0; return n; };
+    while (steps < max_iter && n_active() > 0) {
+        const int batch = std::min(RELAX_AHEAD, max_iter - steps);
+        for (int k = 0; k < batch; k++) {
+            cudaEvent_t *e = c->ev_ring + 4 * k;
+            JF_CUDA(cudaEventRecord(e[0], c->stream));
+            if ((rc = jf_launch_cg(c, cg_tol, cg_maxiter, step, 1))) return rc;
+            JF_CUDA(cudaEventRecord(e[1], c->stream));
+            if ((rc = jf_launch_element(c))) return rc;
+            JF_CUDA(cudaEventRecord(e[2], c->stream));
+            if ((rc = jf_launch_assembly(c))) return rc;
+            JF_CUDA(cudaEventRecord(e[3], c->stream));
         }
-        if (changed) {
-            // only the `active` words change; state values on the device stay as they are
-            for (int s = 0; s < S; s++)
-                JF_CUDA(cudaMemcpyAsync(&c->d_state[s].active, &c->h_state[s].active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        JF_CUDA(cudaEventSynchronize(c->ev_ring[4 * (batch - 1) + 3]));
+        for (int k = 0; k < batch; k++) {
+            cudaEvent_t *e = c->ev_ring + 4 * k;
+            float a = 0, b = 0, d = 0;
+            JF_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
+            JF_CUDA(cudaEventElapsedTime(&b, e[1], e[2]));
+            JF_CUDA(cudaEventElapsedTime(&d, e[2], e[3]));
+            c->stats.ms_cg += a;
+            c->stats.ms_element += b;
+            c->stats.ms_assembly += d;
         }
+        steps += batch;
     }
     JF_CUDA(cudaEventRecord(c->ev[6], c->stream));
-    JF_CUDA(cudaEventSynchronize(c->ev[6]));
+    if ((rc = fetch_state(c))) return rc;   // energies etc. of the final state for the getters; synchronises the stream
     float total = 0;
     JF_CUDA(cudaEventElapsedTime(&total, c->ev[5], c->ev[6]));
     c->stats.ms_relax += total;
+    for (int s = 0; s < S; s++) {
+        const int rows = flags[2 * s];
+        const double *src = progress_rows(c, s);
+        n_iter[s] = rows - 1;
+        for (int i = 0; i < rows; i++) {
+            double *row = relrec + s * stride + 3 * (size_t)i;
+            row[0] = src[4 * i];
+            row[1] = src[4 * i + 1];
+            row[2] = src[4 * i + 2];
+            if (i > 0) {
+                if (cg_iters) cg_iters[(size_t)s * max_iter + (i - 1)] = (int32_t)src[4 * i + 3];
+                c->stats.cg_iterations += (int64_t)src[4 * i + 3];
+            }
+        }
+        c->stats.newton_steps += rows - 1;
+        c->stats.tet_updates += (int64_t)(rows - 1) * c->T;
+        c->h_state[s].active = 1;   // (the device flag is reset by the next jf_relax / jf_evaluate)
+    }
+    return JF_OK;
+}
+
+// Rows of the relaxation record the device has logged so far for system `sys` (a jf_relax running in ANOTHER thread
+// fills them; no CUDA call here): copies up to max_rows rows of (du, energy, residual^2) into `rows` and returns
+// their number in *n_rows.  saenopy rewrites relrec.txt and calls its callback after every Newton step
+// (simulation.py:167); the Python side polls this to do the same while the GPU runs ahead.
+extern "C" int jf_relax_progress(jf_ctx *c, int sys, int32_t *n_rows, double *rows, int max_rows) {
+    if (!c || !n_rows) { jf_set_error("null argument"); return JF_ERR_ARG; }
+    CHECK_SYS(c, sys);
+    if (!c->h_progress) { *n_rows = 0; return JF_OK; }
+    const volatile int *flags = progress_flags(c);
+    int n = flags[2 * sys];
+    if (n > c->rlog.cap) n = c->rlog.cap;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (rows) {
+        const double *src = progress_rows(c, sys);
+        const int m = std::min(n, max_rows);
+        for (int i = 0; i < m; i++)
+            for (int k = 0; k < 3; k++) rows[3 * i + k] = src[4 * i + k];
+        n = m;
+    }
+    *n_rows = n;
     return JF_OK;
 }
 

@@ -79,7 +79,7 @@ constexpr int RED_THREADS = 256;
 __global__ void __launch_bounds__(RED_THREADS) jf_reduce_kernel(const int4 *__restrict__ tets, const double *__restrict__ Et, const double *__restrict__ f,
                                                                 const double *__restrict__ b, jf_sys_state *__restrict__ state,
                                                                 double *__restrict__ partial, unsigned *__restrict__ ticket, long long N,
-                                                                long long Nf, long long Nf_pad, long long T) {
+                                                                long long Nf, long long Nf_pad, long long T, jf_relax_log rl) {
     const int s = blockIdx.y;
     if (!state[s].active) return;
     __shared__ double sm[3][RED_THREADS];
@@ -122,13 +122,52 @@ __global__ void __launch_bounds__(RED_THREADS) jf_reduce_kernel(const int4 *__re
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (threadIdx.x < 3) {
-        const volatile double *p = partial + (long long)s * RED_CTAS * 3 + threadIdx.x;
+    if (threadIdx.x < 32) {
         double acc = 0.0;
-        for (int k = 0; k < RED_CTAS; k++) acc += p[3 * k];
-        if (threadIdx.x == 0) state[s].energy = acc;
-        if (threadIdx.x == 1) state[s].residual2 = acc;
-        if (threadIdx.x == 2) state[s].force2 = acc;
+        if (threadIdx.x < 3) {
+            const volatile double *p = partial + (long long)s * RED_CTAS * 3 + threadIdx.x;
+            for (int k = 0; k < RED_CTAS; k++) acc += p[3 * k];
+            if (threadIdx.x == 0) state[s].energy = acc;
+            if (threadIdx.x == 1) state[s].residual2 = acc;
+            if (threadIdx.x == 2) state[s].force2 = acc;
+        }
+        const double energy = __shfl_sync(0xffffffffu, acc, 0), resid2 = __shfl_sync(0xffffffffu, acc, 1),
+                     force2 = __shfl_sync(0xffffffffu, acc, 2);
+        // ---- the relaxation driver's bookkeeping, on the device: log the record row of this evaluation and
+        // decide whether the system goes on -- saenopy's rule: after Newton step i > 6, stop when
+        // std(last five energies) / sqrt(5) / mean(last five energies) < rel_conv_crit (numpy's population std; IEEE
+        // operations in the host loop's order, no contraction)
+        if (rl.enabled && threadIdx.x == 0) {
+            const int row = state[s].n_rows;                    // 0: start state, i + 1: after Newton step i
+            if (row < rl.cap) {
+                double *r = rl.rows + ((long long)s * rl.cap + row) * 4;
+                r[0] = row == 0 ? 0.0 : state[s].du;
+                r[1] = energy;
+                r[2] = row == 0 ? force2 : resid2;              // saenopy logs sum f^2 (not f - f_target) for the start row
+                r[3] = row == 0 ? 0.0 : (double)state[s].cg_iters;
+                int go_on = row < rl.max_iter;                  // `row` Newton steps done
+                if (row - 1 > 6) {
+                    double mean = 0.0, var = 0.0;
+                    for (int j = 0; j < 5; j++) mean = __dadd_rn(mean, r[1 - 4 * j]);
+                    mean = __ddiv_rn(mean, 5.0);
+                    for (int j = 0; j < 5; j++) {
+                        const double d = __dadd_rn(r[1 - 4 * j], -mean);
+                        var = __dadd_rn(var, __dmul_rn(d, d));
+                    }
+                    const double estd = __ddiv_rn(__dsqrt_rn(__ddiv_rn(var, 5.0)), __dsqrt_rn(5.0));
+                    if (__ddiv_rn(estd, mean) < rl.conv_crit) go_on = 0;
+                }
+                state[s].n_rows = row + 1;
+                if (!go_on) state[s].active = 0;
+                if (rl.host_rows) {                             // progress for the host (mapped memory): row first, then the count
+                    double *h = rl.host_rows + ((long long)s * rl.cap + row) * 4;
+                    h[0] = r[0]; h[1] = r[1]; h[2] = r[2]; h[3] = r[3];
+                    __threadfence_system();
+                    rl.host_flags[2 * s + 1] = go_on;
+                    rl.host_flags[2 * s] = row + 1;
+                }
+            }
+        }
     }
 }
 
@@ -193,7 +232,7 @@ int jf_launch_assembly(jf_ctx *c) {
                                                   c->Nf, c->Nf_pad, c->T);
     JF_CUDA(cudaGetLastError());
     jf_reduce_kernel<<<dim3(RED_CTAS, (unsigned)c->n_sys), RED_THREADS, 0, c->stream>>>((const int4 *)c->d_tets, c->d_Et, c->d_f, c->d_b, c->d_state, c->d_red_partial,
-                                                                                      c->d_red_ticket, c->N, c->Nf, c->Nf_pad, c->T);
+                                                                                      c->d_red_ticket, c->N, c->Nf, c->Nf_pad, c->T, c->rlog);
     JF_CUDA(cudaGetLastError());
     c->stats.kernel_launches += 2;
     return 0;

@@ -53,7 +53,7 @@ struct FusedShared {
     double normb[F_MAX_SYS], rho[F_MAX_SYS], alpha[F_MAX_SYS], beta[F_MAX_SYS], tot0[F_MAX_SYS];
     int done[F_MAX_SYS], iters[F_MAX_SYS], lastcur[F_MAX_SYS];
     // fixed-point all-reduce (one system): exponents of the previous iteration's p.Ap and Ap.Ap, words to add
-    int expo[2], scale_ok, fallback;
+    int expo[2], expo_ok[2], fallback;  // exponents of the previous p.Ap and Ap.Ap (units of the fixed-point words) and whether they are usable
     unsigned long long word[8];  // 0..5: two limbs of each sum, 6: overflow mark; each with this CTA's arrival in the top bits
 #ifdef JF_FX_CHECK
     double dbg[3], dbg_max;
@@ -171,57 +171,56 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
     fused_collect<NQ, KMAX>(a, sh, part, update);
 }
 
-// alpha, the new r.r, the stop decision, beta and the units of the next fixed-point sums from the three totals of an
-// iteration.  ln < 0: one thread does everything (slot-table path); ln >= 0: called by a whole warp with ln = lane, which
-// shares the serial pieces -- lane 0 divides rho / pAp while lane 1 forms 1 / rho and lanes 2, 3 take the exponents; the
-// dependent chain is one division instead of two.  Both forms execute the same operations on the same inputs, so the
-// two paths agree bit for bit (beta = rsnew * (1 / rho) in both).
+// alpha, beta, the new r.r, the stop decision and the units of the next fixed-point sums from the three totals of an
+// iteration.  With alpha = rho / pAp:
+//       beta = r'.r' / rho = 1 - 2 (r.Ap / p.Ap) + alpha (Ap.Ap / p.Ap)        r'.r' = rho beta
+// -- three quotients by the same total that do not depend on each other.  ln < 0: one thread does everything (slot-table
+// path); ln >= 0: called by a whole warp with ln = lane: lanes 0, 1, 2 divide side by side, lanes 4, 5 take the exponents
+// meanwhile and write them themselves; the dependent chain is one division, two shuffles and three multiply-adds.  Both
+// forms execute the same operations on the same inputs, so the two paths agree bit for bit.
 __device__ __forceinline__ void fused_update_scalars(FusedShared &sh, int ss, double pAp, double rAp, double ApAp, int ln, long long it,
                                                      long long maxiter, double tol, bool want_expo, int cur) {
     if (sh.done[ss]) return;
     const double rho = sh.rho[ss];
-    double alpha, inv_rho;
-    int e = 0;
-    bool eok = true;
+    double alpha, t1, t2;
     if (ln < 0) {
         alpha = rho / pAp;
-        inv_rho = 1.0 / rho;
+        t1 = rAp / pAp;
+        t2 = ApAp / pAp;
     } else {
-        const double qv = (ln == 1 ? 1.0 : rho) / (ln == 1 ? rho : pAp);
-        if (want_expo && (ln == 2 || ln == 3)) eok = fx_exponent_ok(ln == 3 ? ApAp : pAp, &e);
+        const double qv = (ln == 1 ? rAp : ln == 2 ? ApAp : rho) / pAp;
+        if (want_expo && (ln == 4 || ln == 5)) {  // units of the next iteration's fixed-point sums
+            int e = 0;
+            const bool ok = fx_exponent_ok(ln == 5 ? ApAp : pAp, &e);
+            sh.expo[ln - 4] = e;
+            sh.expo_ok[ln - 4] = ok;
+        }
         alpha = __shfl_sync(0xffffffffu, qv, 0);
-        inv_rho = __shfl_sync(0xffffffffu, qv, 1);
+        t1 = __shfl_sync(0xffffffffu, qv, 1);
+        t2 = __shfl_sync(0xffffffffu, qv, 2);
     }
-    const double rsnew = fma(alpha * alpha, ApAp, fma(-2.0 * alpha, rAp, rho));  // r'.r' without a second pass
     if (ln <= 0) {
+        const double beta = fma(alpha, t2, fma(-2.0, t1, 1.0));
+        const double rsnew = rho * beta;  // r'.r' without a second pass over the vectors
         sh.alpha[ss] = alpha;
         sh.iters[ss] = (int)it;
         sh.lastcur[ss] = cur;  // streaming kernel: generation that holds this iteration's p
         if (rsnew < tol * sh.normb[ss] || it == maxiter || !(rsnew > 0.0)) {
             sh.done[ss] = 1;  // the pending x += alpha p is applied after the loop
         } else {
-            sh.beta[ss] = rsnew * inv_rho;
+            sh.beta[ss] = beta;
             sh.rho[ss] = rsnew;
         }
-    }
-    if (!want_expo) return;
-    if (ln < 0) {  // units of the next iteration's fixed-point sums
-        int e0 = 0, e2 = 0;
-        const bool ok = fx_exponent_ok(pAp, &e0) & fx_exponent_ok(ApAp, &e2);
-        sh.expo[0] = e0;
-        sh.expo[1] = e2;
-        sh.scale_ok = ok;
-    } else {
-        const unsigned okm = __ballot_sync(0xffffffffu, eok);
-        if (ln == 2) sh.expo[0] = e;
-        if (ln == 3) sh.expo[1] = e;
-        if (ln == 0) sh.scale_ok = okm == 0xffffffffu;
+        if (want_expo && ln < 0) {
+            int e0 = 0, e2 = 0;
+            sh.expo_ok[0] = fx_exponent_ok(pAp, &e0);
+            sh.expo_ok[1] = fx_exponent_ok(ApAp, &e2);
+            sh.expo[0] = e0;
+            sh.expo[1] = e2;
+        }
     }
 }
 
-// the slot-table all-reduce of one iteration of the loops below, out of line: it runs in the first iteration (no scale
-// yet), when a partial sum does not fit the fixed-point words, and for lockstep batches -- keeping it out of the hot
-// loop's instruction stream
 struct SlotCounters { unsigned epoch, light_target; };
 struct FxPrev { unsigned long long w0 = 0, w1 = 0; };  // per lane: value of its accumulator word when the set's previous use completed
 template <int KMAX>
@@ -273,8 +272,9 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
     unsigned long long *acc = a.acc + (xe & 1u) * 8;
     __syncthreads();  // the warps' partials are in sh.warp; every Ap store of this CTA has been issued
     FMARK(3);
-    if (warp == 0) {
-        // lanes 8q .. 8q+7 add the (at most eight) warp partials of sum q: the same shuffle tree as warp_sum over 8 lanes
+    // lanes 8q .. 8q+7 of one warp add the (at most eight) warp partials of sum q -- the same shuffle tree as warp_sum over 8
+    // lanes -- and lanes 0, 8, 16 turn the three sums into words; then lanes 0..6 hold the words they add
+    auto make_words = [&]() -> unsigned long long {
         const int q = lane >> 3, wsrc = lane & 7;
         double x = (q < 3 && wsrc < nwarps) ? sh.warp[q][0][wsrc] : 0.0;
         x += __shfl_xor_sync(0xffffffffu, x, 4);
@@ -295,24 +295,37 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
                 lo = __double2ll_rd(rem * pow2(FX_LO_SHIFT - E));
                 lo = min(max(lo, 0ll), (1ll << FX_BITS) - 1);
             }
-            sh.word[2 * q] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
-            sh.word[2 * q + 1] = (1ull << FX_COUNT_SHIFT) + (unsigned long long)lo;
         }
         const unsigned bad = __ballot_sync(0xffffffffu, !ok);
-        if (lane == 0) sh.word[6] = (1ull << FX_COUNT_SHIFT) + (bad ? 1ull : 0ull);  // the overflow mark arrives like a sum
+        const unsigned long long whi = (1ull << FX_COUNT_SHIFT) + (unsigned long long)(hi + (1ll << (FX_BITS - 1)));
+        const unsigned long long wlo = (1ull << FX_COUNT_SHIFT) + (unsigned long long)lo;
+        const int src = (lane >> 1) << 3;  // lane 2q and 2q+1 take the words of sum q from lane 8q
+        const unsigned long long a_hi = __shfl_sync(0xffffffffu, whi, src & 31), a_lo = __shfl_sync(0xffffffffu, wlo, src & 31);
+        if (lane == 6) return (1ull << FX_COUNT_SHIFT) + (bad ? 1ull : 0ull);  // the overflow mark arrives like a sum
+        return (lane & 1) ? a_lo : a_hi;
+    };
+    if (warp == 0 && fenced) {
+        const unsigned long long wd = make_words();
+        if (lane < 7) sh.word[lane] = wd;
         __syncwarp();
         named_bar_arrive(1, 64);            // words are in shared memory (bar.arrive orders the stores before it)
-        if (fenced) named_bar_sync(2, blockDim.x);  // every CTA has arrived
+        named_bar_sync(2, blockDim.x);      // every CTA has arrived
         request();
     } else if (warp == 1) {
-        if (fenced && lane == 0) fence_release_gpu();  // this CTA's rows (and slot partials) are in L2 before its words arrive
-        __syncwarp();
-        FMARK(4);
-        named_bar_sync(1, 64);
+        unsigned long long wd;
+        if (fenced) {                       // the fence and the conversion run side by side in two warps
+            if (lane == 0) fence_release_gpu();  // this CTA's rows (and slot partials) are in L2 before its words arrive
+            __syncwarp();
+            FMARK(4);
+            named_bar_sync(1, 64);
+            wd = lane < 7 ? sh.word[lane] : 0ull;
+        } else {
+            wd = make_words();              // nothing to wait for: this warp converts and adds
+        }
         FMARK(5);
         unsigned long long w = 0, raw = 0;  // lanes 0..6: the accumulator words (6: overflow marks), this use's share of them
         const unsigned long long before = (xe & 1u) ? prev.w1 : prev.w0;
-        if (lane < 7) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(sh.word[lane]) : "memory");
+        if (lane < 7) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(wd) : "memory");
         if (!fenced) request();
         bool complete;
         do {
@@ -405,7 +418,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
         sh.alpha[threadIdx.x] = 0.0;
         sh.beta[threadIdx.x] = 0.0;
     }
-    if (threadIdx.x == 0) sh.scale_ok = sh.fallback = 0;
+    if (threadIdx.x == 0) sh.expo_ok[0] = sh.expo_ok[1] = sh.fallback = 0;
 #ifdef JF_FX_CHECK
     if (threadIdx.x == 0) { sh.dbg_max = 0.0; sh.dbg_n = 0; }
 #endif
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 }
             }
         };
-        if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {  // the same decision in every CTA: scale_ok comes from shared totals
+        if (a.exact_sums && a.n_sys == 1 && sh.expo_ok[0] && sh.expo_ok[1]) {  // the same decision in every CTA: it comes from shared totals
             fused_fx_allreduce<5>(a, sh, epoch, xe, fx_prev, light_target, a.fenced != 0, it, true, 0, update, prefetch_halo FT_PASS);
         } else {
             const SlotCounters sc = fused_slot_allreduce<5>(a, &sh, epoch, light_target, it, true, 0);
@@ -707,7 +720,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
         sh.beta[threadIdx.x] = 0.0;
         sh.lastcur[threadIdx.x] = 1;
     }
-    if (threadIdx.x == 0) sh.scale_ok = sh.fallback = 0;
+    if (threadIdx.x == 0) sh.expo_ok[0] = sh.expo_ok[1] = sh.fallback = 0;
     for (int i = threadIdx.x; i < 3 * F_MAX_SYS * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
     __syncthreads();
 
@@ -843,7 +856,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
         auto update = [&](int ss, double pAp, double rAp, double ApAp, int ln) {
             fused_update_scalars(sh, ss, pAp, rAp, ApAp, ln, it, a.maxiter, a.tol, a.n_sys == 1, cur);
         };
-        if (a.exact_sums && a.n_sys == 1 && sh.scale_ok) {
+        if (a.exact_sums && a.n_sys == 1 && sh.expo_ok[0] && sh.expo_ok[1]) {
 #ifdef JF_CG_TIMING
             long long tacc[14], tlast = 0;
 #endif

@@ -76,7 +76,20 @@ struct jf_sys_state {
     double resid;       // CG: r.r carried between iterations
     int cg_iters;       // CG iterations of the last solve
     int active;         // 1 = still relaxing
-    int pad[2];
+    int n_rows;         // relaxation-record rows logged by the device-side driver (jf_reduce_kernel) in this jf_relax
+    int pad;
+};
+
+// what the device-side relaxation driver needs (jf_reduce_kernel logs one record row per evaluation and applies the
+// five-energy stop rule itself, so the host can enqueue Newton steps ahead instead of reading the state every step)
+struct jf_relax_log {
+    double *rows;            // (S, cap, 4) device: du, energy, residual^2 (row 0: sum f^2), CG iterations
+    double *host_rows;       // the same, mapped pinned host memory (written by the kernel; polled by jf_relax_progress)
+    int *host_flags;         // (S, 2) mapped: rows logged, still active
+    int cap;                 // rows per system
+    int max_iter;            // Newton steps allowed
+    double conv_crit;
+    int enabled;
 };
 
 struct jf_ctx {
@@ -141,6 +154,13 @@ struct jf_ctx {
     double curve_r_inner = 0.0;
     uint16_t *d_lcol = nullptr;
     size_t cg_res_smem = 0;
+
+    // device-side relaxation driver
+    jf_relax_log rlog = {};
+    double *d_relrec = nullptr;
+    void *h_progress = nullptr;   // mapped pinned block from the process-wide cache (jf_api.cu)
+    size_t h_progress_bytes = 0;
+    cudaEvent_t ev_ring[4 * 8] = {};
 
     bool have_material = false, evaluated = false;
     std::vector<char> have_targets;

@@ -161,23 +161,45 @@ class Solver:
             raise RuntimeError("nodes and tetrahedra must be set before solving")
         if self.material_model is None:
             raise RuntimeError("material model must be set before solving")
-        out = _lib.solve_boundarycondition(m.nodes, m.tetrahedra, m.movable, m.forces_target, m.displacements,
-                                           self.material_model.as_tuple(), step_size, max_iterations, rel_conv_crit,
-                                           beams=self.beams, device=self.device)
+        if relrecname is None and callback is None and not verbose:
+            out = _lib.solve_boundarycondition(m.nodes, m.tetrahedra, m.movable, m.forces_target, m.displacements,
+                                               self.material_model.as_tuple(), step_size, max_iterations, rel_conv_crit,
+                                               beams=self.beams, device=self.device)
+        else:
+            out = self._solve_with_progress(step_size, max_iterations, rel_conv_crit, relrecname, verbose, callback)
         m.displacements = out["U"]
         m.forces = out["forces"]
         m.strain_energy = float(out["relrec"][-1, 1])
         self.relrec = out["relrec"]
         self.cg_iterations = out["cg_iters"]
         self.stats = out["stats"]
-        if relrecname is not None:
-            np.savetxt(relrecname, self.relrec)
-        if verbose:
-            for i, row in enumerate(self.relrec[1:]):
-                print("Newton ", i, ": du=", row[0], "  Energy=", row[1], "  Residuum=", row[2])
-        if callback is not None:
-            callback(self, self.relrec, len(self.relrec) - 2, max_iterations)
         return self.relrec
+
+    def _solve_with_progress(self, step_size, max_iterations, rel_conv_crit, relrecname, verbose, callback):
+        """saenopy rewrites ``relrecname`` and calls ``callback(self, relrec, i, max_iterations)`` after EVERY Newton
+        step (a killed solve leaves its record behind; progress bars move).  The device logs the record rows into
+        mapped memory while the host keeps enqueueing steps; this thread follows the rows and does both."""
+        m = self.mesh
+        done = [0]
+
+        def on_rows(_sys, rows):
+            self.relrec = rows
+            if relrecname is not None:
+                np.savetxt(relrecname, rows)
+            for i in range(max(done[0], 1), len(rows)):
+                if verbose:
+                    print("Newton ", i - 1, ": du=", rows[i, 0], "  Energy=", rows[i, 1], "  Residuum=", rows[i, 2])
+                if callback is not None:
+                    callback(self, rows[: i + 1], i - 1, max_iterations)
+            done[0] = len(rows)
+        with _lib.Context(m.nodes, np.ascontiguousarray(m.tetrahedra, dtype=np.int32), m.movable, n_sys=1, beams=self.beams,
+                          device=self.device) as ctx:
+            ctx.set_material(*self.material_model.as_tuple())
+            ctx.set_targets(m.forces_target)
+            ctx.set_displacements(m.displacements)
+            relrec, cgit, n = ctx.relax(step_size, max_iterations, rel_conv_crit, on_progress=on_rows)
+            return dict(U=ctx.displacements(), forces=ctx.forces(), relrec=relrec[0], cg_iters=cgit[0], n_iter=int(n[0]),
+                        stats=ctx.stats())
 
     # ---- persistence (simulation.py:168, 278-291) -------------------------------------------------------
     def save(self, filename, layout="saenopy"):

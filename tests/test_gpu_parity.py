@@ -172,7 +172,10 @@ def test_lockstep_batch_equals_single_solves(beams, monkeypatch):
             assert np.array_equal(ctx.displacements(s), singles_slot[s]["U"])  # same kernels, same order: bitwise
             assert np.array_equal(relrec[s], singles_slot[s]["relrec"])
             assert n[s] == singles[s]["n_iter"]
-            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < 5e-5
+            # noise floor of this 360-node case: the oracle on 8 threads differs from the oracle on 1 thread by 1.1e-4
+            # at 1 Pa (3.5e-5 at 100 Pa, 1e-5 at 3 kPa), the kernel variants from each other and from the oracle by
+            # 0.2-1.8e-4 / 0.5-3e-5 / 0.3-2e-5 (tools/trajectory_noise.py); the BASELINE-size meshes sit at 1e-5
+            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < 3e-4
 
 
 def test_bitwise_reproducible(beams):
