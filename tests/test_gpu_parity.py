@@ -347,7 +347,7 @@ def test_batch_of_two_systems(beams, streamed, monkeypatch):
             # (the streamed run also differs from the singles in kernel: CG's loose stop makes the iteration count
             # rounding-sensitive, DESIGN.md "Trajectory sensitivity")
             assert np.abs(cgit[s].astype(int) - singles[s]["cg_iters"]).max() <= (0.15 * singles[s]["cg_iters"].max() if streamed else 2)
-            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < (1e-4 if streamed else 2e-5)
+            assert np.linalg.norm(ctx.displacements(s) - singles[s]["U"]) / np.linalg.norm(singles[s]["U"]) < (5e-4 if streamed else 2e-5)   # streamed: another kernel, 30 unconverged steps (noise floor below)
             # thirty early-stopped, unconverged steps after a differently rounded reduction: the noise floor of such
             # iterates is a few 1e-4 (1.7e-4 measured); it shrinks as the relaxation converges (5e-5 at the stop rule,
             # test_lockstep_batch_equals_single_solves)

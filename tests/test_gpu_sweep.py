@@ -166,3 +166,66 @@ def test_sweep_files_equal_reference_files(ref_sim, tmp_path):
     populated = ~np.isnan(ref_sim["table_y"][0])
     assert np.array_equal(~np.isnan(table["y"][0]), populated)           # same bins populated
     assert np.all(np.diff(table["y"][:, populated], axis=0) > 0)
+
+
+def test_relrec_file_and_callback_follow_the_newton_steps(tmp_path, beams):
+    """saenopy rewrites `relrecname` and calls `callback(solver, relrec, i, max_iterations)` after EVERY Newton step
+    (what simulation.py:167 relies on for relrec.txt).  The device logs the rows while the host enqueues steps ahead;
+    the caller's thread follows them: callbacks arrive for i = 0 .. n-1 in order with a growing record, and the file
+    always holds the rows seen so far."""
+    from conftest import make_case
+    case = make_case(0.2, 100.0)                          # config-1 size: ~90 Newton steps, ~0.1 s
+    M = jf.simulation.Solver()
+    M.set_material_model(jf.simulation.SemiAffineFiberMaterial(*COLLAGEN12))
+    M.set_nodes(case["coords"]); M.set_tetrahedra(case["tets"])
+    M.set_boundary_condition(case["bc"]["displacement"], case["bc"]["forces"])
+    name = str(tmp_path / "relrec.txt")
+    calls, rows_in_file = [], []
+
+    def cb(solver, relrec, i, max_iterations):
+        calls.append((i, len(relrec), max_iterations))
+        rows_in_file.append(len(np.atleast_2d(np.loadtxt(name))))
+    rr = M.solve_boundarycondition(step_size=0.0033, max_iterations=600, rel_conv_crit=0.01, relrecname=name, callback=cb)
+    n = len(rr) - 1
+    assert [c[0] for c in calls] == list(range(n)) and all(c[2] == 600 for c in calls)
+    assert [c[1] for c in calls] == list(range(2, n + 2))                      # start row + one row per finished step
+    assert all(r >= c[1] for r, c in zip(rows_in_file, calls))                  # the file is never behind the callback
+    assert len({r for r in rows_in_file}) > 3                                   # it really was rewritten while the solve ran
+    assert np.array_equal(np.loadtxt(name), rr)
+    # and the same solve without progress reporting gives the same bits
+    M2 = jf.simulation.Solver()
+    M2.set_material_model(jf.simulation.SemiAffineFiberMaterial(*COLLAGEN12))
+    M2.set_nodes(case["coords"]); M2.set_tetrahedra(case["tets"])
+    M2.set_boundary_condition(case["bc"]["displacement"], case["bc"]["forces"])
+    rr2 = M2.solve_boundarycondition(step_size=0.0033, max_iterations=600, rel_conv_crit=0.01)
+    assert np.array_equal(rr, rr2) and np.array_equal(M.mesh.displacements, M2.mesh.displacements)
+
+
+def test_killed_solve_leaves_its_relaxation_record(tmp_path):
+    """A solve killed half way (SIGKILL: no cleanup runs) has written relrec.txt for the steps it finished -- the
+    reference gets this from saenopy's np.savetxt after every iteration."""
+    import signal
+    import subprocess
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    name = str(tmp_path / "relrec.txt")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, jointforces_b200 as jf\n"
+            "from conftest import make_case, COLLAGEN12\n"
+            "c = make_case(0.1, 100.0)\n"                  # config-4 size: a second or so of relaxation
+            "M = jf.simulation.Solver(); M.set_material_model(jf.simulation.SemiAffineFiberMaterial(*COLLAGEN12))\n"
+            "M.set_nodes(c['coords']); M.set_tetrahedra(c['tets']); M.set_boundary_condition(c['bc']['displacement'], c['bc']['forces'])\n"
+            "print('go', flush=True)\n"
+            "M.solve_boundarycondition(step_size=0.0033, max_iterations=600, rel_conv_crit=0.01, relrecname=%r)\n"
+            "print('done', flush=True)\n" % (root, os.path.join(root, "tests"), name))
+    proc = subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, text=True)
+    assert proc.stdout.readline().strip() == "go"
+    deadline = time.time() + 60
+    while time.time() < deadline and not (os.path.exists(name) and os.path.getsize(name) > 300):
+        time.sleep(0.01)
+    proc.send_signal(signal.SIGKILL)
+    proc.wait()
+    assert proc.returncode == -signal.SIGKILL
+    rows = np.atleast_2d(np.loadtxt(name))
+    assert 2 <= len(rows) < 78 and rows.shape[1] == 3 and rows[0, 0] == 0 and np.all(rows[1:, 1] > 0)
