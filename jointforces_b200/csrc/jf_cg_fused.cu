@@ -253,10 +253,11 @@ __device__ __noinline__ SlotCounters fused_slot_allreduce(CgArgs a, FusedShared 
 //                   the complete counts -> bar -> `request()`.  The formally ordered path (JF_CG_FENCED=1, and always
 //                   for the streaming kernel, whose rows carry no tag).
 // The overflow mark travels in a seventh word that carries its own arrival count, so "complete" covers it.
-template <int KMAX, typename U, typename P>
+template <int KMAX, bool NEVER_FENCED = false, typename U, typename P>
 __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared &sh, unsigned &epoch, unsigned &xe, FxPrev &prev,
-                                                   unsigned &light_target, bool fenced, long long it, bool want_expo, int cur, U update,
+                                                   unsigned &light_target, bool fenced_arg, long long it, bool want_expo, int cur, U update,
                                                    P request FT_ARGS) {
+    const bool fenced = !NEVER_FENCED && fenced_arg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     epoch++;
     xe++;
@@ -288,7 +289,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
         if (q < 3 && wsrc == 0) {
             const int E = sh.expo[q == 2 ? 1 : 0];
             ok = fabs(x) < pow2(E + FX_HEADROOM) &&  // false for NaN
-                 !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0);
+                 (NEVER_FENCED || !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0));
             if (ok) {
                 hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
                 const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi]; rounds only for tiny negative x, by < 2^-9 low units
@@ -384,14 +385,21 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
 #endif
 }
 
+// FAST = the default single-solve path as a specialisation of its own: one system, halo requests ahead, fixed-point sums,
+// tagged rows (no fence), every CTA's foreign halo within one round of loads.  The iteration is bound by the issue
+// latency of a lone warp's dependent instructions (ncu: 2 warps per scheduler, ~6 cycles per instruction, every branch
+// ~20), so what the general kernel decides at run time -- loops over systems, rounds of halo loads, mode switches --
+// is compiled away here.  Same arithmetic, same bits (test_resident_and_streaming_cg_agree, JF_CG_GENERAL=1 selects the
+// general instantiation).
+template <bool FAST>
 __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ FusedShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = blockDim.x >> 6;  // slices per CTA (two warps per 32-row slice)
-    const int s = blockIdx.x / a.ctas_per_sys;
-    const int cb = blockIdx.x - s * a.ctas_per_sys;
+    const int s = FAST ? 0 : blockIdx.x / a.ctas_per_sys;
+    const int cb = FAST ? blockIdx.x : blockIdx.x - s * a.ctas_per_sys;
     const int half = lane >> 4;
     const int rloc = warp * 16 + (lane & 15);
     const long long sl = (long long)cb * W + (rloc >> 5);
@@ -509,11 +517,15 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
 #pragma unroll
     for (int k = 0; k < F_HALO_BATCH; k++) pre[k] = make_double4(0.0, 0.0, 0.0, tag_of(0));
     for (long long it = 1; it <= a.maxiter; it++) {
-        int all = 1;
-        for (int q = 0; q < a.n_sys; q++) all &= sh.done[q];
-        if (all) break;
+        if (FAST) {
+            if (sh.done[0]) break;
+        } else {
+            int all = 1;
+            for (int q = 0; q < a.n_sys; q++) all &= sh.done[q];
+            if (all) break;
+        }
         FMARK(0);
-        const bool on = !sh.done[s];
+        const bool on = FAST || !sh.done[s];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         if (on) {
             const double alpha = sh.alpha[s], beta = sh.beta[s];  // of the previous iteration (0, 0 for the first)
@@ -541,7 +553,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             }
             // (the shared-memory loads of a stage are issued before its first store: hr and hp could alias for all the
             //  compiler knows, and a load placed behind a store would wait for it)
-            for (int hb = n_own + threadIdx.x; hb < nh; hb += F_HALO_BATCH * blockDim.x) {
+            for (int hb = n_own + threadIdx.x; hb < nh; hb += FAST ? (1 << 30) : F_HALO_BATCH * blockDim.x) {
                 double4 av[F_HALO_BATCH];
                 double rn[F_HALO_BATCH][3], po[F_HALO_BATCH][3];
                 int hh[F_HALO_BATCH];
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 for (int k = 0; k < F_HALO_BATCH; k++) {
                     const int h = hb + k * blockDim.x;
                     hh[k] = h < nh ? h : hb;
-                    av[k] = (hb == n_own + (int)threadIdx.x && a.prefetch) ? pre[k] : ld_node_l2(Ao + hn[hh[k]]);
+                    av[k] = (FAST || (hb == n_own + (int)threadIdx.x && a.prefetch)) ? pre[k] : ld_node_l2(Ao + hn[hh[k]]);
                 }
 #pragma unroll
                 for (int k = 0; k < F_HALO_BATCH; k++)
@@ -626,7 +638,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
         };
         auto prefetch_halo = [&]() {
             // the next iteration's first round of halo loads (this iteration's Ap) travels while the scalars are formed
-            if (on && nh > 0 && a.prefetch) {
+            if (FAST || (on && nh > 0 && a.prefetch)) {
                 const double4 *An_c = cur ? A_1 : A_0;
 #pragma unroll
                 for (int k = 0; k < F_HALO_BATCH; k++) {
@@ -635,8 +647,8 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
                 }
             }
         };
-        if (a.exact_sums && a.n_sys == 1 && sh.expo_ok[0] && sh.expo_ok[1]) {  // the same decision in every CTA: it comes from shared totals
-            fused_fx_allreduce<5>(a, sh, epoch, xe, fx_prev, light_target, a.fenced != 0, it, true, 0, update, prefetch_halo FT_PASS);
+        if ((FAST || (a.exact_sums && a.n_sys == 1)) && sh.expo_ok[0] && sh.expo_ok[1]) {  // the same decision in every CTA: it comes from shared totals
+            fused_fx_allreduce<5, FAST>(a, sh, epoch, xe, fx_prev, light_target, !FAST && a.fenced != 0, it, true, 0, update, prefetch_halo FT_PASS);
         } else {
             const SlotCounters sc = fused_slot_allreduce<5>(a, &sh, epoch, light_target, it, true, 0);
             epoch = sc.epoch;
@@ -915,9 +927,12 @@ int jf_cg_fused_configure(jf_ctx *c) {
     // the collect keeps five partial sums per lane in registers: at most 160 CTAs (B200: 148 SMs)
     if (c->cg_resident != 2 || c->n_sys > F_MAX_SYS || c->cg_grid > 160 || getenv("JF_CG_CLASSIC")) return 0;
     const size_t smem = (size_t)c->cg_hmax * (6 * sizeof(double) + sizeof(int)) + (size_t)c->cg_res_warps * 64 * (9 * sizeof(double) + sizeof(int));
-    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_kernel, c->cg_res_warps * 64, smem));
+    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, per_sm_fast = 0;
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_kernel<false>, c->cg_res_warps * 64, smem));
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, jf_cg_fused_kernel<true>, c->cg_res_warps * 64, smem));
+    if (per_sm_fast < 1) per_sm = 0;
     if (per_sm < 1) return 0;
     c->cg_fused_smem = smem;
     c->cg_fused = 1;
@@ -978,7 +993,11 @@ int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
     a.r1 = c->d_r1;
     a.Ap1 = c->d_Ap1;
     void *args[] = {&a};
-    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_fused_kernel, dim3(c->cg_grid), dim3(c->cg_res_warps * 64), args, c->cg_fused_smem,
-                                        c->stream));
+    // the specialised instantiation where its assumptions hold (see the kernel): one system, default switches, one round
+    // of halo loads per thread
+    const bool fast = c->n_sys == 1 && a.prefetch && a.exact_sums && a.light_barrier && !a.fenced && a.fx_test == 0 &&
+                      c->cg_foreign_max <= F_HALO_BATCH * c->cg_res_warps * 64 && getenv("JF_CG_GENERAL") == nullptr;
+    JF_CUDA(cudaLaunchCooperativeKernel(fast ? (void *)jf_cg_fused_kernel<true> : (void *)jf_cg_fused_kernel<false>, dim3(c->cg_grid),
+                                        dim3(c->cg_res_warps * 64), args, c->cg_fused_smem, c->stream));
     return 0;
 }

@@ -433,8 +433,11 @@ int jf_cg_resident_configure(jf_ctx *c) {
             }
         }
     }, 8);
+    c->cg_foreign_max = 0;
     for (int cb = 0; cb < ctas; cb++) {
         if (lists[cb].size() > 65535) return 0;
+        const int64_t own = (std::min<int64_t>(c->n_slices, (int64_t)(cb + 1) * W) - (int64_t)cb * W) * JF_SLICE;
+        c->cg_foreign_max = std::max(c->cg_foreign_max, (int)((int64_t)lists[cb].size() - own));
         hnodes.insert(hnodes.end(), lists[cb].begin(), lists[cb].end());
         hptr[cb + 1] = (int32_t)hnodes.size();
         hmax = std::max(hmax, (int)lists[cb].size());
