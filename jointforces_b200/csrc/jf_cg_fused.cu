@@ -74,8 +74,8 @@ __device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &targ
         __threadfence();  // (red.release.gpu compiles to the same MEMBAR + REDG sequence)
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned seen;
-        do {  // acquire: pairs with the arrivals' fence + red (LDG.STRONG.GPU + CCTL.IVALL; this kernel keeps nothing in L1)
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        do {  // relaxed poll; what is read from other CTAs afterwards comes from L2 (ld.global.cg), see fused_fx_allreduce
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
         } while (seen < target);
     }
     __syncthreads();
@@ -331,7 +331,10 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
         bool complete;
         do {
             if (lane < 7) {
-                if (fenced) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane) : "memory");
+                // (acquire = LDG.STRONG.GPU + CCTL.IVALL: an L1 invalidation per poll, which costs the streaming kernel 13 % --
+                //  it keeps its index arrays in L1; everything read from other CTAs afterwards is loaded with ld.global.cg,
+                //  i.e. from L2, so the invalidation buys nothing on this hardware.  JF_CG_ACQUIRE=1 asks for it anyway.)
+                if (fenced && a.acquire) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane) : "memory");
                 else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane) : "memory");
             }
             w = raw - before;
@@ -961,6 +964,7 @@ int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
     a.light_barrier = getenv("JF_CG_CGSYNC") == nullptr;
     a.exact_sums = a.light_barrier && getenv("JF_CG_SLOT_SUMS") == nullptr;
     a.fx_test = getenv("JF_FX_TEST_OVERFLOW") ? atoi(getenv("JF_FX_TEST_OVERFLOW")) : 0;
+    a.acquire = getenv("JF_CG_ACQUIRE") != nullptr;
     a.acc = (unsigned long long *)((char *)c->d_sync + 64);
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
@@ -979,7 +983,8 @@ int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
     const bool no_prefetch = getenv("JF_CG_NO_PREFETCH") != nullptr, cg_sync = getenv("JF_CG_CGSYNC") != nullptr,
                slot_sums = getenv("JF_CG_SLOT_SUMS") != nullptr;
     a.prefetch = !no_prefetch;
-    a.fenced = getenv("JF_CG_FENCED") != nullptr;  // order the Ap rows by fence/acquire instead of relying on their tags
+    a.fenced = getenv("JF_CG_FENCED") != nullptr;  // order the Ap rows by a release fence instead of relying on their tags
+    a.acquire = getenv("JF_CG_ACQUIRE") != nullptr;
     a.launch_seq = (int)(++c->cg_launch_seq & 0x7fffffff);
     a.light_barrier = !cg_sync;
     a.exact_sums = !slot_sums && !cg_sync;
