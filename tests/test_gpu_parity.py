@@ -523,3 +523,31 @@ def test_golden_oracle_table_rows(beams):
         ok = ~np.isnan(g["curves"][i])
         assert np.array_equal(np.isnan(r["curve"]), ~ok)
         assert np.max(np.abs(r["curve"][ok] / g["curves"][i][ok] - 1)) < 1e-3, i
+
+
+def test_single_reduction_kernel_orderings_agree_bitwise(beams, monkeypatch):
+    """The register-resident single-reduction kernel in its three forms -- specialised instantiation with self-validating
+    (tagged) Ap rows and no fence (default), the general instantiation (JF_CG_GENERAL=1), and fence-ordered rows
+    (JF_CG_FENCED=1, with and without acquire polling) -- executes the same arithmetic: any row read before it arrived,
+    or read torn, would change bits.  Repeated to give a race more than one chance."""
+    from jointforces_b200 import _lib
+    c = make_case(0.2, 300.0)                  # config-1 size: register-resident kernel, ~80 CTAs
+    outs = {}
+    for label, env in (("default", {}), ("general", {"JF_CG_GENERAL": "1"}), ("fenced", {"JF_CG_FENCED": "1"}),
+                       ("fenced+acquire", {"JF_CG_FENCED": "1", "JF_CG_ACQUIRE": "1"}), ("default again", {})):
+        for k in ("JF_CG_GENERAL", "JF_CG_FENCED", "JF_CG_ACQUIRE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams) as ctx:
+            assert (ctx.info()["cg_resident"], ctx.info()["cg_fused"]) == (2, 1)
+            ctx.set_material(*COLLAGEN12)
+            ctx.set_targets(c["f_target"])
+            ctx.set_displacements(np.zeros_like(c["coords"]))
+            relrec, cgit, n = ctx.relax(0.0033, 40, 0.01)
+            outs[label] = (ctx.displacements(), relrec[0], cgit[0])
+    ref = outs["default"]
+    for label, o in outs.items():
+        assert np.array_equal(o[2], ref[2]), label
+        assert np.array_equal(o[1], ref[1]), label
+        assert np.array_equal(o[0], ref[0]), label
