@@ -171,11 +171,17 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         for (auto &e : c->ev_ring)
             if (cudaEventCreate(&e) != cudaSuccess) { rc = jf_cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
         if (rc) break;
-        {   // keep freed workspace in the pool for the next context
+        {   // Keep freed workspace in the device's default stream-ordered pool for the next context (a sweep creates and
+            // destroys contexts; cudaMalloc/cudaFree cost 30-250 ms per context).  This raises the release threshold of a
+            // pool the host application may share: the memory stays reserved until cudaMemPoolTrimTo or process exit.
+            // JF_POOL_KEEP_MB bounds it (default: 8192 MB); JF_POOL_KEEP_MB=0 leaves the pool's threshold alone.
             cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            const char *env = getenv("JF_POOL_KEEP_MB");
+            const unsigned long long keep_mb = env ? strtoull(env, nullptr, 10) : 8192ull;
+            if (keep_mb > 0 && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = keep_mb << 20, cur = 0;
+                if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
         }
         StageTimer tm;

@@ -89,13 +89,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- all-reduce through integer atomics that double as the grid barrier (one system) --------------------------
-// Each of the three sums is accumulated exactly as an 88-bit fixed-point number in two 64-bit words (44 bits each, the
-// high part biased to stay non-negative); every addend also adds 1 to the top ten bits of its word, so a word whose
-// top bits equal the number of CTAs is complete: arrival and data are the same atomic, and one poll of two sectors
-// replaces the barrier's poll plus the separate read of 3 x grid partial sums.  The unit is 2^-23 (high) and 2^-67
-// (low) of 2^E, E = exponent of the previous iteration's total (all CTAs derive it from the same bits), so a partial
-// may be 2^19 times larger than the previous total before it does not fit; such an iteration falls back to the slot
-// tables, which are always written too.  Integer addition is order independent: bitwise reproducible by construction.
+// Each of the three sums is accumulated as an 88-bit fixed-point number in two 64-bit words (44 bits each, the high part
+// biased to stay non-negative); every addend also adds 1 to the top ten bits of its word, so a word whose top bits have
+// advanced by the number of CTAs is complete: arrival and data are the same atomic, and one poll of two sectors replaces
+// the barrier's poll plus the separate read of 3 x grid partial sums.  The unit is 2^-23 (high) and 2^-67 (low) of 2^E,
+// E = exponent of the previous iteration's total (all CTAs derive it from the same bits), so a partial may be 2^19 times
+// larger than the previous total before it does not fit; such a partial raises a mark in a seventh word (which carries
+// its own arrival count, so a complete poll has seen every mark) and the iteration is reduced again through the slot
+// tables -- written only then.  Integer addition is order independent: bitwise reproducible by construction.
+// Precision: every partial is truncated to the low unit (2^-67 of 2^E: far below a double's ulp of the total unless the
+// total collapses by more than 2^14 against the previous one -- then the sum still carries 53 - log2(collapse) + 14
+// bits, and CG's next iteration re-derives the scale); the decode rounds twice.  tests/test_fixed_point_model.py restates
+// encode / accumulate / decode with Python integers.
 constexpr int FX_COUNT_SHIFT = 54;  // arrivals in the top 10 bits: grids of up to 1023 CTAs
 constexpr int FX_BITS = 44;         // bits per limb: 1023 biased limbs stay below 2^54
 constexpr int FX_HEADROOM = 19;

@@ -5,7 +5,7 @@
 // the mesh only, so the caller classifies the nodes once (same float comparisons as numpy) and
 // hands over the per-bin node lists; per solve one CTA per (system, bin) computes the norms with
 // numpy's operation order (no FMA contraction, IEEE sqrt and divide) and selects the median by
-// rank counting -- bit-identical to np.nanmedian on the same displacements.  D2H per load case
+// rank counting over the non-NaN entries -- bit-identical to np.nanmedian on the same displacements.  D2H per load case
 // drops from N*24 bytes to n_bins*8.
 #include <math.h>
 
@@ -31,11 +31,25 @@ __global__ void __launch_bounds__(256) jf_curve_kernel(const int32_t *__restrict
         v[i] = __ddiv_rn(__dsqrt_rn(q), r_inner);
     }
     __syncthreads();
-    // rank selection: element i has rank = #{j : v_j < v_i} + #{j < i : v_j == v_i}; ranks are a permutation
-    const int k_hi = n / 2, k_lo = (n - 1) / 2;  // middle element(s): equal for odd n
+    // np.nanmedian: NaN entries (a diverged solve) are left out; a bin without any finite-or-infinite entry gives NaN.
+    // Rank selection over the m non-NaN entries: element i has rank = #{j : v_j < v_i} + #{j < i : v_j == v_i}; the ranks
+    // of the non-NaN elements are a permutation of 0..m-1 (comparisons with NaN are false, so NaNs never count).
     __shared__ double mid[2];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    __shared__ int n_valid;
+    if (threadIdx.x == 0) {
+        mid[0] = mid[1] = nan("");
+        n_valid = 0;
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += v[i] == v[i];
+    if (mine) atomicAdd(&n_valid, mine);
+    __syncthreads();
+    const int m = n_valid;
+    const int k_hi = m / 2, k_lo = (m - 1) / 2;  // middle element(s): equal for odd m
+    for (int i = threadIdx.x; i < n && m > 0; i += blockDim.x) {
         const double vi = v[i];
+        if (vi != vi) continue;
         int rank = 0;
         for (int j = 0; j < n; j++) {
             const double vj = v[j];
@@ -45,7 +59,8 @@ __global__ void __launch_bounds__(256) jf_curve_kernel(const int32_t *__restrict
         if (rank == k_hi) mid[1] = vi;
     }
     __syncthreads();
-    if (threadIdx.x == 0) out[(long long)s * n_bins + bin] = (k_lo == k_hi) ? mid[0] : __dmul_rn(__dadd_rn(mid[0], mid[1]), 0.5);
+    if (threadIdx.x == 0)
+        out[(long long)s * n_bins + bin] = m == 0 ? nan("") : ((k_lo == k_hi) ? mid[0] : __dmul_rn(__dadd_rn(mid[0], mid[1]), 0.5));
 }
 
 }  // namespace
