@@ -192,7 +192,9 @@ def spherical_contraction_solver(meshfile, outfolder, pressure, material, r_inne
                               relrecname=outfolder + "/relrec.txt")
     M.save(outfolder + "/solver.saenopy")
     # the legacy archive the reference's last loader fallback reads with any saenopy version (:252-258, 289-291)
-    M.save(outfolder + "/solver.npz", layout="legacy")
+    save_legacy = getattr(M, "save_legacy", None)   # (an object with saenopy's own Solver protocol has no such method)
+    if save_legacy is not None:
+        save_legacy(outfolder + "/solver.npz")
     return M
 
 

@@ -206,6 +206,10 @@ class Solver:
         save_solver_file(filename, self.mesh.nodes, self.mesh.tetrahedra, self.mesh.displacements, self.mesh.forces,
                          self.mesh.forces_target, self.mesh.movable, self.material_parameters, self.relrec, layout=layout)
 
+    def save_legacy(self, filename):
+        """The pre-1.0 archive (keys ``R, T, U, f``) that ``simulation.py:252-258, 289-291`` falls back to."""
+        self.save(filename, layout="legacy")
+
     # legacy attribute names (simulation.py:213, 286-287)
     @property
     def R(self):
@@ -240,7 +244,7 @@ class Solver:
 def _material_list(material_parameters):
     """saenopy's ``material.serialize()``: ``['SemiAffineFiberMaterial', k, d_0, lambda_s, d_s]`` (rebuilt on load with
     ``SemiAffineFiberMaterial(*material_parameters[1:])``)."""
-    if material_parameters is None:
+    if material_parameters is None or len(material_parameters) == 0:
         return None
     if isinstance(material_parameters, dict):
         m = material_parameters
