@@ -8,8 +8,9 @@ Default workload ``cfg3`` = BASELINE configs[2], the lookup-table sweep the metr
 B200" is quoted on: collagen12 on the configs[1] mesh (17,612 nodes / 102,744 tets), pressures from
 ``np.logspace(-1, 4, 150)``.  One "step" relaxes every fifth pressure of that table (30 solves, all three
 material regimes; five consecutive steps cover the table once) and gathers the 30 curve rows.  STRONG scaling:
-the 30 solves of a step are spread over the N ranks (shared work counter in the process group's store), the
-rows gathered over NCCL at the end of every step.
+the K steps of the timed region are ONE work list (K x 30 load cases, step after step) that the N ranks draw from
+a shared counter in the process group's store -- a rank that is done with step j goes on with step j+1 -- and the rows
+are gathered over NCCL at the end, as for a real 150-pressure table (one gather per table).
 
   value   sims/hour, whole job, device time: per step the max over ranks of the CUDA-event time of its
           relaxations (jf_relax), mesh structure resident in HBM
@@ -45,7 +46,7 @@ WORKLOADS = {
     "cfg1": ("configs[0]: spherical_inclusion lf=0.2 (lf_iso 0.2), linear K_0=2364, 100 Pa", None, 0.2, "linear2364", 100.0),
     "cfg2": ("configs[1]: spherical_inclusion lf=0.05 (lf_iso 0.1667), collagen12, 100 Pa, single solve", 0.05, None, "collagen12", 100.0),
     "cfg3": ("configs[2]: collagen12 lookup-table sweep on the configs[1] mesh, np.logspace(-1,4,150); one step = every 5th "
-             "pressure (30 solves), offset rotating with the step", 0.05, None, "collagen12", None),
+             "pressure (30 solves), offset rotating with the step; the steps of the timed region form one work list", 0.05, None, "collagen12", None),
     "cfg4": ("configs[3]: spherical_inclusion lf=0.03 (lf_iso 0.1), collagen24, 10 kPa", 0.03, None, "collagen24", 10000.0),
     "cfg5": ("configs[4]: spherical_inclusion lf=0.015 (lf_iso 0.05), collagen06, 100 Pa", 0.015, None, "collagen06", 100.0),
 }
@@ -469,46 +470,53 @@ def main():
         info = engine.info()
         costs_all = jsweep.pressure_cost(TABLE, mat_dict)
 
-        def device_step(j):
-            idx = step_indices(j)
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            order = idx[np.argsort(-costs_all[idx], kind="stable")]
-            claimer = jsweep._Claimer(order, costs_all[order], rank, world, "dynamic")
-            ms, rows, done = 0.0, [], []
+        def device_region(j0, nsteps):
+            """`nsteps` steps as ONE work list (step after step, the most expensive case of a step first), drawn from the
+            shared counter: a rank that finishes its last case of step j goes on with step j+1, so the only idle time is
+            at the end of the region -- the way a real table (150 cases, one gather) is scheduled.  A rank writes the
+            L2-flush buffer whenever it enters a new step.  Returns (max, min) over ranks of the device time and the
+            number of cases this rank relaxed."""
+            flat, step_of = [], []
+            for j in range(j0, j0 + nsteps):
+                idx = step_indices(j)
+                flat += [int(i) for i in idx[np.argsort(-costs_all[idx], kind="stable")]]
+                step_of += [j] * len(idx)
+            flat = np.asarray(flat)
+            claimer = jsweep._Claimer(np.arange(len(flat)), costs_all[flat], rank, world, "dynamic")
+            ms, rows, done, last_step = 0.0, [], [], None
             while True:
                 chunk = claimer.take(engine.batch)
                 if not chunk:
                     break
-                forces = [spherical_boundary_conditions(case["coords"], R_IN, R_OUT, float(TABLE[i]))["forces"] for i in chunk]
-                for i, res in zip(chunk, engine.relax_batch(forces, fetch_fields=False)):
+                if step_of[chunk[0]] != last_step:
+                    last_step = step_of[chunk[0]]
+                    flush.fill_(1)
+                    torch.cuda.synchronize()
+                cases = [int(flat[q]) for q in chunk]
+                forces = [spherical_boundary_conditions(case["coords"], R_IN, R_OUT, float(TABLE[i]))["forces"] for i in cases]
+                for q, res in zip(chunk, engine.relax_batch(forces, fetch_fields=False)):
                     ms += res["ms"]
                     rows.append(res["curve"])
-                    done.append(i)
-            jsweep.gather_table(done, TABLE[done], np.asarray(rows).reshape(len(done), -1), len(TABLE), len(x_edges) - 1, device=local)
+                    done.append(q)
+            jsweep.gather_table(done, TABLE[flat[done]] if done else [], np.asarray(rows).reshape(len(done), -1), len(flat),
+                                len(x_edges) - 1, device=local)
             t = torch.tensor([ms, -ms], dtype=torch.float64, device="cuda")
             if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)      # (max, -min) of the ranks' device time for this step
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)      # (max, -min) of the ranks' device time
             return float(t[0].item()), -float(t[1].item()), len(done)
 
-        for j in range(W):
-            device_step(j)
+        device_region(0, W)
         engine.totals = None
         sampler = ClockSampler(local)
         barrier()
         sampler.start()
         t_wall0 = time.time()
-        ms_max = ms_min = 0.0
-        mine = 0
-        for j in range(K):
-            a, b, n_mine = device_step(W + j)
-            ms_max += a
-            ms_min += b
-            mine += n_mine
+        ms_max, ms_min, mine = device_region(W, K)
         barrier()
         wall = time.time() - t_wall0
         clocks = sampler.stop()
-        st = engine.totals or {}
+        st = engine.totals or {k: 0.0 for k in ("kernel_launches", "tet_updates", "cg_iterations", "cg_launches")}
+        st.update({k: st.get(k) or 1e-9 for k in ("ms_element", "ms_assembly", "ms_cg")})   # (a rank that drew no case)
         engine.close()
         S = len(step_indices(0))
         value = K * S * 3600.0 / (ms_max * 1e-3)
@@ -527,11 +535,15 @@ def main():
             write_msh22(meshfile, case["coords"], case["tets"], 100, 10000, case["length_factor"])
         barrier()
 
-        def e2e_step(j):
-            out = os.path.join(tmp, "sweep%d" % j)
+        def e2e_call(j0, nsteps):
+            """ONE run_sweep call (the call a user makes) over the pressures of `nsteps` steps -- the whole 150-pressure
+            table when nsteps = 5."""
+            out = os.path.join(tmp, "sweep%d" % j0)
+            values = np.concatenate([TABLE[step_indices(j)] for j in range(j0, j0 + nsteps)])
+            flush.fill_(1)
             barrier()
             t0 = time.time()
-            table = jsweep.run_sweep(meshfile, out, TABLE[step_indices(j)], mat_dict, max_iter=SOLVER["max_iter"], step=SOLVER["step"],
+            table = jsweep.run_sweep(meshfile, out, values, mat_dict, max_iter=SOLVER["max_iter"], step=SOLVER["step"],
                                      conv_crit=SOLVER["conv_crit"])
             barrier()
             dt = time.time() - t0
@@ -539,15 +551,11 @@ def main():
                 shutil.rmtree(out, ignore_errors=True)
             return dt, table
 
-        e2e_step(0)
-        Ke = min(K, 5)
-        e2e_s, h2d, d2h = 0.0, 0.0, 0.0
-        for j in range(Ke):
-            flush.fill_(1)
-            dt, table = e2e_step(W + j)
-            e2e_s += dt
-            h2d += table["stats"]["bytes_h2d"] if table["stats"] else 0
-            d2h += table["stats"]["bytes_d2h"] if table["stats"] else 0
+        e2e_call(0, 1)
+        Ke = min(K, STRIDE)
+        e2e_s, table = e2e_call(W, Ke)
+        h2d = table["stats"]["bytes_h2d"] if table["stats"] else 0
+        d2h = table["stats"]["bytes_d2h"] if table["stats"] else 0
         tt = torch.tensor([e2e_s, h2d, d2h], dtype=torch.float64, device="cuda")
         if world > 1:
             mx = tt[:1].clone()
@@ -563,7 +571,8 @@ def main():
         line.update(value=value, ms_per_step=ms_max / K, scaling="strong", clocks=clocks,
                     e2e={"value": Ke * S * 3600.0 / e2e_s, "unit": "sims/hour", "h2d_bytes_per_step": int(h2d / Ke),
                          "d2h_bytes_per_step": int(d2h / Ke), "ms_per_step": e2e_s * 1e3 / Ke, "steps": Ke,
-                         "path": "run_sweep: msh file -> structure -> H2D -> 30 relaxations -> D2H -> folders written -> gather"},
+                         "path": "one run_sweep call over %d pressures: msh file -> structure -> H2D -> relaxations -> D2H -> folders "
+                                 "written -> gather" % (Ke * S)},
                     gpu_launches=int(launches.item()),
                     submetrics={"tet_updates_per_s": st["tet_updates"] / (st["ms_element"] * 1e-3),
                                 "cg_iters_per_s": st["cg_iterations"] / (st["ms_cg"] * 1e-3),

@@ -113,7 +113,7 @@ static void ctx_free(jf_ctx *c) {
                     c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_halo_ptr, c->d_halo_nodes, c->d_lcol, c->d_bin_ptr, c->d_bin_nodes, c->d_curve_scratch,
                     c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_r1, c->d_Ap1, c->d_partial, c->d_sync, c->d_red_partial, c->d_red_ticket,
-                    c->d_relrec};
+                    c->d_relrec, c->d_acc};
     if (c->stream) {
         for (void *p : ptrs)
             if (p) cudaFreeAsync(p, c->stream);
@@ -216,6 +216,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if ((rc = jf_dev_alloc(c, &c->d_partial, 64 * S * (size_t)std::max(c->cg_grid, c->cg_fused_stream_grid)))) break;  // (2 parities, <= 8 replicas, <= 3 sums, S, grid)
         // barrier counter (16 B), 3 x 8 fixed-point accumulators at byte 64, then (2, S, grid) 16-byte slots at byte 256
         if ((rc = jf_dev_alloc(c, &c->d_sync, 64 + 8 * S * (size_t)c->cg_grid))) break;
+        if ((rc = jf_dev_alloc(c, &c->d_acc, 16 * JF_ACC_MAX_STRIDE))) break;
         if ((rc = jf_dev_alloc(c, &c->d_red_partial, S * 32 * 3))) break;
         if ((rc = jf_dev_alloc(c, &c->d_red_ticket, S))) break;
         cudaMemsetAsync(c->d_red_ticket, 0, S * sizeof(unsigned), c->stream);  // counter + (2, S, grid) 16-byte slots

@@ -49,6 +49,7 @@ struct CgArgs {
     int light_barrier = 1;      // single-reduction kernel: counter barrier without the L1 invalidation (JF_CG_CGSYNC=1: grid.sync)
     int prefetch = 1;           // single-reduction kernel: request the halo Ap ahead of its use (JF_CG_NO_PREFETCH=1: off)
     int fenced = 0;             // register-resident single-reduction kernel: fence/acquire ordering of the Ap rows (JF_CG_FENCED=1)
+    int acc_stride = 1;         // 64-bit words between two accumulator words of the fixed-point all-reduce (JF_CG_ACC_STRIDE)
     int acquire = 0;            // fenced ordering: poll with ld.acquire (L1 invalidation per poll) instead of ld.relaxed (JF_CG_ACQUIRE=1)
     int launch_seq = 0;         // CG launches of this context so far: upper half of the Ap rows' epoch tag
 };

@@ -46,6 +46,9 @@ constexpr int F_HALO_BATCH = 2;  // one round of loads covers 512 foreign halo n
 #ifndef F_REPLICAS
 #define F_REPLICAS 4
 #endif
+#ifndef JF_ACC_DEFAULT_STRIDE
+#define JF_ACC_DEFAULT_STRIDE 1
+#endif
 constexpr int F_MAX_SYS = 16;   // systems per launch in this kernel (shared tables are sized by it)
 
 struct FusedShared {
@@ -275,7 +278,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
     // the difference to the value the set had when its previous use completed (`prev`, the same in every CTA because a
     // set is complete -- and stays untouched until everyone has read it -- when a CTA leaves the poll).  Nothing has to
     // be ordered against a clearing store.
-    unsigned long long *acc = a.acc + (xe & 1u) * 8;
+    unsigned long long *acc = a.acc + (size_t)(xe & 1u) * 8 * a.acc_stride;
     __syncthreads();  // the warps' partials are in sh.warp; every Ap store of this CTA has been issued
     FMARK(3);
     // lanes 8q .. 8q+7 of one warp add the (at most eight) warp partials of sum q -- the same shuffle tree as warp_sum over 8
@@ -331,7 +334,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
         FMARK(5);
         unsigned long long w = 0, raw = 0;  // lanes 0..6: the accumulator words (6: overflow marks), this use's share of them
         const unsigned long long before = (xe & 1u) ? prev.w1 : prev.w0;
-        if (lane < 7) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane), "l"(wd) : "memory");
+        if (lane < 7) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane * a.acc_stride), "l"(wd) : "memory");
         if (!fenced) request();
         bool complete;
         do {
@@ -339,8 +342,8 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
                 // (acquire = LDG.STRONG.GPU + CCTL.IVALL: an L1 invalidation per poll, which costs the streaming kernel 13 % --
                 //  it keeps its index arrays in L1; everything read from other CTAs afterwards is loaded with ld.global.cg,
                 //  i.e. from L2, so the invalidation buys nothing on this hardware.  JF_CG_ACQUIRE=1 asks for it anyway.)
-                if (fenced && a.acquire) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane) : "memory");
-                else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane) : "memory");
+                if (fenced && a.acquire) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane * a.acc_stride) : "memory");
+                else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane * a.acc_stride) : "memory");
             }
             w = raw - before;
             complete = lane >= 7 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
@@ -965,12 +968,27 @@ int jf_cg_fused_stream_configure(jf_ctx *c) {
     return 1;
 }
 
+// JF_CG_ACC_STRIDE=n (64-bit words, power of two <= JF_ACC_MAX_STRIDE): the seven accumulator words of a set on separate
+// lines, so their atomics are served by different L2 slices instead of queueing on two sectors of one
+static void fused_place_accumulators(jf_ctx *c, CgArgs &a) {
+    const char *e = getenv("JF_CG_ACC_STRIDE");
+    int stride = e ? atoi(e) : JF_ACC_DEFAULT_STRIDE;
+    if (stride < 1 || stride > JF_ACC_MAX_STRIDE) stride = 1;
+    a.acc_stride = stride;
+    if (stride == 1) {
+        a.acc = (unsigned long long *)((char *)c->d_sync + 64);  // zeroed with the barrier counter (jf_launch_cg)
+    } else {
+        a.acc = c->d_acc;
+        cudaMemsetAsync(c->d_acc, 0, (size_t)16 * stride * sizeof(unsigned long long), c->stream);
+    }
+}
+
 int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
     a.light_barrier = getenv("JF_CG_CGSYNC") == nullptr;
     a.exact_sums = a.light_barrier && getenv("JF_CG_SLOT_SUMS") == nullptr;
     a.fx_test = getenv("JF_FX_TEST_OVERFLOW") ? atoi(getenv("JF_FX_TEST_OVERFLOW")) : 0;
     a.acquire = getenv("JF_CG_ACQUIRE") != nullptr;
-    a.acc = (unsigned long long *)((char *)c->d_sync + 64);
+    fused_place_accumulators(c, a);
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;
@@ -994,7 +1012,7 @@ int jf_cg_fused_launch(jf_ctx *c, CgArgs &a) {
     a.light_barrier = !cg_sync;
     a.exact_sums = !slot_sums && !cg_sync;
     a.fx_test = getenv("JF_FX_TEST_OVERFLOW") ? atoi(getenv("JF_FX_TEST_OVERFLOW")) : 0;
-    a.acc = (unsigned long long *)((char *)c->d_sync + 64);
+    fused_place_accumulators(c, a);
     a.halo_ptr = c->d_halo_ptr;
     a.halo_nodes = c->d_halo_nodes;
     a.lcol = c->d_lcol;

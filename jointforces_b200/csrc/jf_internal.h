@@ -140,6 +140,7 @@ struct jf_ctx {
     size_t cg_fused_smem = 0;
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
     double *d_red_partial = nullptr;   // (S, 32, 3) partial sums of jf_reduce_kernel
+    unsigned long long *d_acc = nullptr;  // fixed-point accumulators on separate lines (JF_CG_ACC_STRIDE > 1)
     unsigned *d_red_ticket = nullptr;  // (S) arrival tickets of jf_reduce_kernel (self-resetting)
     unsigned int *d_sync = nullptr;    // barrier counter (16 B), fixed-point accumulators (byte 64), sums-only slots (byte 256)
     int cg_grid = 0, elem_grid = 0;
@@ -171,6 +172,8 @@ struct jf_ctx {
     // host copies kept for the parity hooks
     std::vector<int32_t> h_sell_col, h_slice_ptr, h_rowlen;
 };
+
+constexpr int JF_ACC_MAX_STRIDE = 1024;  // words between two fixed-point accumulator words (JF_CG_ACC_STRIDE)
 
 // jf_setup.cu
 int jf_build_structure(jf_ctx *c, const double *nodes, const int32_t *tets, const uint8_t *movable,
