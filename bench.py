@@ -140,6 +140,8 @@ def cg_bytes_per_iteration(info):
 
 
 def cg_kernel_name(info):
+    if info.get("cg_fused") == 4:
+        return "jf_cg_pair_kernel"
     if info.get("cg_fused") == 1:
         return "jf_cg_fused_kernel"
     if info.get("cg_fused") == 2:
@@ -162,15 +164,17 @@ def roofline_of(info, st, peaks, peak_kind, workload):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    resident = bool(info["cg_resident"])
+    resident = bool(info["cg_resident"]) or info.get("cg_fused") == 4
     matrix_mb = info["n_blocks"] * 72 / 1e6
     return {"bound": "latency" if resident else "hbm", "nominal_bound": "hbm", "kernel": cg_kernel_name(info), "achieved": achieved,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
             "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": by_iter * st["cg_iterations"] / max(1, st["cg_launches"]),
             "us_per_cg_iteration": st["ms_cg"] * 1e3 / max(1, st["cg_iterations"]),
-            "achieved_is": ("a rate of algorithmic bytes: the %.0f MB matrix is staged once per CG solve into registers / shared "
-                            "memory, DRAM is idle (`traffic`); the iteration is bound by its grid-wide all-reduce. "
-                            "roofline_large is the HBM-bound regime" % matrix_mb) if resident else "HBM traffic (matrix streamed)"}
+            "achieved_is": ("a rate of algorithmic bytes: the %.0f MB matrix of a system is staged once per CG solve into registers / "
+                            "shared memory, DRAM is idle (`traffic`); the iteration is bound by its grid-wide all-reduce%s. "
+                            "roofline_large is the HBM-bound regime"
+                            % (matrix_mb, " (two systems per launch, two CTAs per SM: us_per_cg_iteration is per system-iteration)"
+                               if info.get("cg_fused") == 4 else "")) if resident else "HBM traffic (matrix streamed)"}
 
 
 def hbm_regime_leg(device, peaks):

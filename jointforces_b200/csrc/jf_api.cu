@@ -113,7 +113,7 @@ static void ctx_free(jf_ctx *c) {
                     c->d_U0, c->d_Et, c->d_fel, c->d_Kel, c->d_slice_ptr, c->d_sell_col, c->d_contrib_ptr, c->d_contrib_src,
                     c->d_fn_ptr, c->d_fn_src, c->d_halo_ptr, c->d_halo_nodes, c->d_lcol, c->d_bin_ptr, c->d_bin_nodes, c->d_curve_scratch,
                     c->d_curves, c->d_val, c->d_b, c->d_x, c->d_r, c->d_p0, c->d_p1, c->d_Ap, c->d_r1, c->d_Ap1, c->d_partial, c->d_sync, c->d_red_partial, c->d_red_ticket,
-                    c->d_relrec, c->d_acc};
+                    c->d_relrec, c->d_acc, c->d_pair_halo_ptr, c->d_pair_halo_nodes, c->d_pair_lcol};
     if (c->stream) {
         for (void *p : ptrs)
             if (p) cudaFreeAsync(p, c->stream);
@@ -213,7 +213,7 @@ extern "C" int jf_ctx_create(jf_ctx **out, int device, int n_sys, int64_t n_node
         if ((rc = jf_cg_configure(c))) break;
         tm.mark("cg configure");
         if ((rc = jf_elem_configure(c))) break;
-        if ((rc = jf_dev_alloc(c, &c->d_partial, 64 * S * (size_t)std::max(c->cg_grid, c->cg_fused_stream_grid)))) break;  // (2 parities, <= 8 replicas, <= 3 sums, S, grid)
+        if ((rc = jf_dev_alloc(c, &c->d_partial, std::max<size_t>(64 * S * (size_t)std::max(c->cg_grid, c->cg_fused_stream_grid), 2 * 8192)))) break;  // (2 parities, <= 8 replicas, <= 3 sums, S, grid)
         // barrier counter (16 B), 3 x 8 fixed-point accumulators at byte 64, then (2, S, grid) 16-byte slots at byte 256
         if ((rc = jf_dev_alloc(c, &c->d_sync, 64 + 8 * S * (size_t)c->cg_grid))) break;
         if ((rc = jf_dev_alloc(c, &c->d_acc, 16 * JF_ACC_MAX_STRIDE))) break;
@@ -691,7 +691,7 @@ extern "C" int jf_get_info(jf_ctx *c, jf_info *o) {
     o->cg_resident = c->cg_resident;
     o->cg_wmax = c->cg_wmax;
     o->cg_stream_halo = c->cg_stream_halo;
-    o->cg_fused = c->cg_fused + 2 * c->cg_fused_stream;  // 1: register-resident, 2: streaming single-reduction kernel
+    o->cg_fused = c->cg_pair ? 4 : c->cg_fused + 2 * c->cg_fused_stream;  // 1: register-resident, 2: streaming single-reduction kernel, 4: two systems side by side
     return JF_OK;
 }
 

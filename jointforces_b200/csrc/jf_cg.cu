@@ -43,13 +43,17 @@ int jf_cg_fused_configure(jf_ctx *c);
 int jf_cg_fused_launch(jf_ctx *c, CgArgs &a);
 int jf_cg_fused_stream_configure(jf_ctx *c);
 int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a);
+int jf_cg_pair_configure(jf_ctx *c);
+int jf_cg_pair_launch(jf_ctx *c, CgArgs &a);
 
 // Streamed matrices that are not much larger than the L2 (BASELINE configs[3]: 92 MB of blocks against 126 MB) are
-// read once per CG iteration and evicted by the vectors and by their own tail before the next iteration comes round
-// (ncu, round 1: 66 % L2 hits, 33 MB per iteration from DRAM).  An access-policy window marks the matrix as persisting
-// in the set-aside part of L2, so the iterations after the first find it there.  JF_NO_L2_WINDOW=1 switches it off.
+// read once per CG iteration and partly evicted by the vectors and by their own tail before the next iteration comes
+// round (ncu, round 1: 66 % L2 hits, 33 MB per iteration from DRAM).  An access-policy window that marks the matrix as
+// persisting in the set-aside part of L2 was tried for that: measured twice on config 4, it is SLOWER than leaving the
+// replacement policy alone (19.65 vs 18.28 and 19.96 vs 19.42 us per iteration, profiles/README.md r2u/r2x -- the
+// set-aside takes L2 away from the vectors and the gathered halo), so it is opt-in: JF_L2_WINDOW=1.
 static int jf_cg_l2_window(jf_ctx *c) {
-    if (c->cg_resident || getenv("JF_NO_L2_WINDOW")) return 0;
+    if (c->cg_resident || !getenv("JF_L2_WINDOW")) return 0;
     int max_persist = 0, max_window = 0;
     if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device) != cudaSuccess ||
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device) != cudaSuccess || max_persist <= 0) {
@@ -86,6 +90,9 @@ int jf_cg_configure(jf_ctx *c) {
     if (rc) return rc;
     rc = jf_cg_fused_stream_configure(c);
     if (rc < 0) return rc;
+    rc = jf_cg_pair_configure(c);  // two systems of a config-2-size mesh: side by side, matrices on chip
+    if (rc < 0) return rc;
+    if (rc == 1) return 0;
     return jf_cg_l2_window(c);
 }
 
@@ -126,9 +133,11 @@ int jf_launch_cg(jf_ctx *c, double tol, int64_t maxiter, double step, int apply_
     // tolerances go through the classic two-reduction kernels.
     const bool fused = c->cg_fused && tol >= 1e-9;
     const bool fused_stream = c->cg_fused_stream && tol >= 1e-9;
-    int rc = fused ? jf_cg_fused_launch(c, a)
-                   : (c->cg_resident ? jf_cg_resident_launch(c, a)
-                                     : (fused_stream ? jf_cg_fused_stream_launch(c, a) : jf_cg_stream_launch(c, a)));
+    const bool pair = c->cg_pair && tol >= 1e-9;
+    int rc = pair ? jf_cg_pair_launch(c, a)
+                  : (fused ? jf_cg_fused_launch(c, a)
+                           : (c->cg_resident ? jf_cg_resident_launch(c, a)
+                                             : (fused_stream ? jf_cg_fused_stream_launch(c, a) : jf_cg_stream_launch(c, a))));
     if (rc) return rc;
     c->stats.kernel_launches++;
     c->stats.cg_launches++;

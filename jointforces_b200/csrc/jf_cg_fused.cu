@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "jf_cg_common.cuh"
 
@@ -51,10 +52,11 @@ constexpr int F_HALO_BATCH = 2;  // one round of loads covers 512 foreign halo n
 #endif
 constexpr int F_MAX_SYS = 16;   // systems per launch in this kernel (shared tables are sized by it)
 
-struct FusedShared {
-    double warp[3][F_MAX_SYS][8];  // per-warp partials of (p.Ap, r.Ap, Ap.Ap)
-    double normb[F_MAX_SYS], rho[F_MAX_SYS], alpha[F_MAX_SYS], beta[F_MAX_SYS], tot0[F_MAX_SYS];
-    int done[F_MAX_SYS], iters[F_MAX_SYS], lastcur[F_MAX_SYS];
+template <int MS>
+struct FusedSharedT {
+    double warp[3][MS][8];  // per-warp partials of (p.Ap, r.Ap, Ap.Ap)
+    double normb[MS], rho[MS], alpha[MS], beta[MS], tot0[MS];
+    int done[MS], iters[MS], lastcur[MS];
     // fixed-point all-reduce (one system): exponents of the previous iteration's p.Ap and Ap.Ap, words to add
     int expo[2], expo_ok[2], fallback;  // exponents of the previous p.Ap and Ap.Ap (units of the fixed-point words) and whether they are usable
     unsigned long long word[8];  // 0..5: two limbs of each sum, 6: overflow mark; each with this CTA's arrival in the top bits
@@ -63,6 +65,15 @@ struct FusedShared {
     int dbg_n;
 #endif
 };
+using FusedShared = FusedSharedT<F_MAX_SYS>;
+
+// The CTAs that reduce together: the whole grid, or (jf_cg_pair_kernel) the CTAs of one system -- `n` of them, this
+// one being number `i`.  The counters, partial-sum tables and accumulators a group uses come with the CgArgs it passes.
+struct Grp {
+    unsigned n, i;
+    __device__ __forceinline__ Grp() : n(gridDim.x), i(blockIdx.x) {}
+    __device__ __forceinline__ Grp(unsigned n_, unsigned i_) : n(n_), i(i_) {}
+};
 
 // all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order.
 // After it the lane that owns system s's totals runs `update(s, t0, t1, t2)` before the CTA barrier.
@@ -70,10 +81,10 @@ struct FusedShared {
 // the arrival, no L1 invalidation after it -- everything this kernel reads from other CTAs afterwards (halo Ap,
 // partial sums) is loaded from L2 (ld.global.cg), and nothing else it reads changes during the launch.
 // cg::grid.sync() adds MEMBAR + CCTL.IVALL on the way out (8 % of an iteration in the ncu source view).
-__device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &target) {
+__device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &target, unsigned n_ctas) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        target += gridDim.x;
+        target += n_ctas;
         __threadfence();  // (red.release.gpu compiles to the same MEMBAR + REDG sequence)
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         unsigned seen;
@@ -121,42 +132,42 @@ __device__ __forceinline__ bool fx_exponent_ok(double v, int *e) {
 }
 
 // first half: publish the CTA's partial sums and pass the grid barrier
-template <int NQ, bool LIGHT = false>
-__device__ __forceinline__ double *fused_publish_sync(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch,
-                                                      unsigned *light_target = nullptr) {
+template <int NQ, bool LIGHT = false, typename SH>
+__device__ __forceinline__ double *fused_publish_sync(const CgArgs &a, cg::grid_group &grid, SH &sh, unsigned &epoch,
+                                                      unsigned *light_target = nullptr, const Grp grp = Grp()) {
     epoch++;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // F_REPLICAS copies of the partial table: CTA b reads copy b % F_REPLICAS, so a line has fewer simultaneous readers
-    const size_t table = (size_t)3 * a.n_sys * gridDim.x;
+    const size_t table = (size_t)3 * a.n_sys * grp.n;
     double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
     __syncthreads();
     for (int v = warp; v < NQ * a.n_sys; v += nwarps) {
         const int q = v / a.n_sys, s = v - q * a.n_sys;
         double x = lane < nwarps ? sh.warp[q][s][lane] : 0.0;
         x = warp_sum(x);
-        if (lane < F_REPLICAS) part[lane * table + (size_t)v * gridDim.x + blockIdx.x] = x;
+        if (lane < F_REPLICAS) part[lane * table + (size_t)v * grp.n + grp.i] = x;
     }
-    if (LIGHT && a.light_barrier) light_grid_barrier(a.sync_ctr, *light_target);
+    if (LIGHT && a.light_barrier) light_grid_barrier(a.sync_ctr, *light_target, grp.n);
     else grid.sync();
     return part;
 }
 
 // second half: every CTA adds the partial sums in the same order; the lane that owns system s's totals runs
 // `update(s, t0, t1, t2)` before the CTA barrier
-template <int NQ, int KMAX, typename F>
-__device__ __forceinline__ void fused_collect(const CgArgs &a, FusedShared &sh, const double *part, F update) {
+template <int NQ, int KMAX, typename SH, typename F>
+__device__ __forceinline__ void fused_collect(const CgArgs &a, SH &sh, const double *part, F update, const Grp grp = Grp()) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const size_t table = (size_t)3 * a.n_sys * gridDim.x;
+    const size_t table = (size_t)3 * a.n_sys * grp.n;
     for (int s = warp; s < a.n_sys; s += nwarps) {
         // all loads of all sums in flight before the first shuffle (grid <= 32*KMAX CTAs: KMAX per lane and sum)
         double v[3][KMAX];
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-            const double *p = part + (blockIdx.x % F_REPLICAS) * table + (size_t)(q * a.n_sys + s) * gridDim.x;
+            const double *p = part + (grp.i % F_REPLICAS) * table + (size_t)(q * a.n_sys + s) * grp.n;
 #pragma unroll
             for (int k = 0; k < KMAX; k++) {
                 const int i = lane + 32 * k;
-                v[q][k] = i < (int)gridDim.x ? __ldcg(p + i) : 0.0;
+                v[q][k] = i < (int)grp.n ? __ldcg(p + i) : 0.0;
             }
         }
         double t[3] = {0.0, 0.0, 0.0};
@@ -173,10 +184,11 @@ __device__ __forceinline__ void fused_collect(const CgArgs &a, FusedShared &sh, 
 }
 
 // all-reduce of `nq` values per system + grid barrier (cooperative groups), fixed summation order
-template <int NQ, int KMAX, typename F>
-__device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, FusedShared &sh, unsigned &epoch, F update) {
-    const double *part = fused_publish_sync<NQ>(a, grid, sh, epoch);
-    fused_collect<NQ, KMAX>(a, sh, part, update);
+template <int NQ, int KMAX, typename SH, typename F>
+__device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group &grid, SH &sh, unsigned &epoch, F update,
+                                                const Grp grp = Grp()) {
+    const double *part = fused_publish_sync<NQ>(a, grid, sh, epoch, nullptr, grp);
+    fused_collect<NQ, KMAX>(a, sh, part, update, grp);
 }
 
 // alpha, beta, the new r.r, the stop decision and the units of the next fixed-point sums from the three totals of an
@@ -186,7 +198,8 @@ __device__ __forceinline__ void fused_allreduce(const CgArgs &a, cg::grid_group 
 // path); ln >= 0: called by a whole warp with ln = lane: lanes 0, 1, 2 divide side by side, lanes 4, 5 take the exponents
 // meanwhile and write them themselves; the dependent chain is one division, two shuffles and three multiply-adds.  Both
 // forms execute the same operations on the same inputs, so the two paths agree bit for bit.
-__device__ __forceinline__ void fused_update_scalars(FusedShared &sh, int ss, double pAp, double rAp, double ApAp, int ln, long long it,
+template <typename SH>
+__device__ __forceinline__ void fused_update_scalars(SH &sh, int ss, double pAp, double rAp, double ApAp, int ln, long long it,
                                                      long long maxiter, double tol, bool want_expo, int cur) {
     if (sh.done[ss]) return;
     const double rho = sh.rho[ss];
@@ -231,16 +244,16 @@ __device__ __forceinline__ void fused_update_scalars(FusedShared &sh, int ss, do
 
 struct SlotCounters { unsigned epoch, light_target; };
 struct FxPrev { unsigned long long w0 = 0, w1 = 0; };  // per lane: value of its accumulator word when the set's previous use completed
-template <int KMAX>
-__device__ __noinline__ SlotCounters fused_slot_allreduce(CgArgs a, FusedShared *shp, unsigned epoch, unsigned light_target, long long it,
-                                                          bool want_expo, int cur) {
+template <int KMAX, typename SH>
+__device__ __noinline__ SlotCounters fused_slot_allreduce(CgArgs a, SH *shp, unsigned epoch, unsigned light_target, long long it,
+                                                          bool want_expo, int cur, const Grp grp = Grp()) {
     // (arguments by value and the counters returned: a reference parameter would pin the caller's copy to local memory)
-    FusedShared &sh = *shp;
+    SH &sh = *shp;
     cg::grid_group grid = cg::this_grid();
-    const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target);
+    const double *part = fused_publish_sync<3, true>(a, grid, sh, epoch, &light_target, grp);
     fused_collect<3, KMAX>(a, sh, part, [&](int ss, double s0, double s1, double s2) {
         fused_update_scalars(sh, ss, s0, s1, s2, -1, it, a.maxiter, a.tol, want_expo, cur);
-    });
+    }, grp);
     return SlotCounters{epoch, light_target};
 }
 
@@ -261,17 +274,17 @@ __device__ __noinline__ SlotCounters fused_slot_allreduce(CgArgs a, FusedShared 
 //                   the complete counts -> bar -> `request()`.  The formally ordered path (JF_CG_FENCED=1, and always
 //                   for the streaming kernel, whose rows carry no tag).
 // The overflow mark travels in a seventh word that carries its own arrival count, so "complete" covers it.
-template <int KMAX, bool NEVER_FENCED = false, typename U, typename P>
-__device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared &sh, unsigned &epoch, unsigned &xe, FxPrev &prev,
+template <int KMAX, bool NEVER_FENCED = false, typename SH, typename U, typename P>
+__device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, SH &sh, unsigned &epoch, unsigned &xe, FxPrev &prev,
                                                    unsigned &light_target, bool fenced_arg, long long it, bool want_expo, int cur, U update,
-                                                   P request FT_ARGS) {
+                                                   P request, const Grp grp FT_ARGS) {
     const bool fenced = !NEVER_FENCED && fenced_arg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     epoch++;
     xe++;
     const int nwarps = blockDim.x >> 5;
 #ifdef JF_FX_CHECK
-    const size_t table = (size_t)3 * gridDim.x;
+    const size_t table = (size_t)3 * grp.n;
     double *part = a.partial + (size_t)(epoch & 1u) * F_REPLICAS * table;
 #endif
     // Two accumulator sets alternate and are never cleared during a launch: the words only grow, and the sum of one use is
@@ -290,14 +303,14 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
         x += __shfl_xor_sync(0xffffffffu, x, 2);
         x += __shfl_xor_sync(0xffffffffu, x, 1);
 #ifdef JF_FX_CHECK
-        if (q < 3 && wsrc < F_REPLICAS) part[wsrc * table + (size_t)q * gridDim.x + blockIdx.x] = x;
+        if (q < 3 && wsrc < F_REPLICAS) part[wsrc * table + (size_t)q * grp.n + grp.i] = x;
 #endif
         bool ok = true;
         long long hi = 0, lo = 0;
         if (q < 3 && wsrc == 0) {
             const int E = sh.expo[q == 2 ? 1 : 0];
             ok = fabs(x) < pow2(E + FX_HEADROOM) &&  // false for NaN
-                 (NEVER_FENCED || !(a.fx_test > 0 && blockIdx.x == 0 && xe % (unsigned)a.fx_test == 0));
+                 (NEVER_FENCED || !(a.fx_test > 0 && grp.i == 0 && xe % (unsigned)a.fx_test == 0));
             if (ok) {
                 hi = __double2ll_rd(x * pow2(FX_HI_SHIFT - E));
                 const double rem = fma(-(double)hi, pow2(E - FX_HI_SHIFT), x);  // in [0, unit_hi]; rounds only for tiny negative x, by < 2^-9 low units
@@ -346,7 +359,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
                 else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(raw) : "l"(acc + lane * a.acc_stride) : "memory");
             }
             w = raw - before;
-            complete = lane >= 7 || (unsigned)(w >> FX_COUNT_SHIFT) == gridDim.x;
+            complete = lane >= 7 || (unsigned)(w >> FX_COUNT_SHIFT) == grp.n;
 #ifdef JF_CG_TIMING
             if (threadIdx.x == 32) tacc[9]++;
 #endif
@@ -361,7 +374,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
             const unsigned long long body = w & ((1ull << FX_COUNT_SHIFT) - 1);
             const int E = sh.expo[(lane >> 1) == 2 ? 1 : 0];
             if (lane & 1) d = (double)body * pow2(E - FX_LO_SHIFT);
-            else d = (double)((long long)body - (long long)gridDim.x * (1ll << (FX_BITS - 1))) * pow2(E - FX_HI_SHIFT);
+            else d = (double)((long long)body - (long long)grp.n * (1ll << (FX_BITS - 1))) * pow2(E - FX_HI_SHIFT);
         }
         const double t = d + __shfl_down_sync(0xffffffffu, d, 1);  // lanes 0, 2, 4: high + low part
         const double t0 = __shfl_sync(0xffffffffu, t, 0), t1 = __shfl_sync(0xffffffffu, t, 2), t2 = __shfl_sync(0xffffffffu, t, 4);
@@ -381,7 +394,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
     __syncthreads();  // the scalars are in shared memory
     FMARK(7);
     if (sh.fallback) {  // some partial did not fit: this iteration goes through the slot tables (per-warp partials are still in sh.warp)
-        const SlotCounters sc = fused_slot_allreduce<KMAX>(a, &sh, epoch, light_target, it, want_expo, cur);
+        const SlotCounters sc = fused_slot_allreduce<KMAX>(a, &sh, epoch, light_target, it, want_expo, cur, grp);
         epoch = sc.epoch;
         light_target = sc.light_target;
     }
@@ -391,7 +404,7 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, FusedShared 
             const double r0 = fabs(sh.dbg[0] - s0) / fabs(s0), r1 = fabs(sh.dbg[1] - s1) / fabs(s1), r2 = fabs(sh.dbg[2] - s2) / fabs(s2);
             sh.dbg_max = fmax(sh.dbg_max, fmax(r0, fmax(r1, r2)));
             sh.dbg_n++;
-        });
+        }, grp);
     }
 #endif
 }
@@ -659,7 +672,7 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
             }
         };
         if ((FAST || (a.exact_sums && a.n_sys == 1)) && sh.expo_ok[0] && sh.expo_ok[1]) {  // the same decision in every CTA: it comes from shared totals
-            fused_fx_allreduce<5, FAST>(a, sh, epoch, xe, fx_prev, light_target, !FAST && a.fenced != 0, it, true, 0, update, prefetch_halo FT_PASS);
+            fused_fx_allreduce<5, FAST>(a, sh, epoch, xe, fx_prev, light_target, !FAST && a.fenced != 0, it, true, 0, update, prefetch_halo, Grp() FT_PASS);
         } else {
             const SlotCounters sc = fused_slot_allreduce<5>(a, &sh, epoch, light_target, it, true, 0);
             epoch = sc.epoch;
@@ -712,6 +725,309 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
         a.state[q].normb = sh.normb[q];
         a.state[q].resid = sh.rho[q];
         if (a.apply_update) a.state[q].du = a.step * a.step * sh.tot0[q];
+    }
+}
+
+// =================================================================================================
+// Two load cases of one mesh side by side (sweeps): jf_cg_pair_kernel.
+//
+// The single-solve kernel above leaves an SM idle for the ~60 % of an iteration its one CTA spends in the grid-wide
+// all-reduce, and it cannot share the SM: its 256 threads x 255 registers are the whole register file.  Here a CTA is
+// 128 threads -- ONE thread per block row, four slices -- so two CTAs fit an SM (2 x 128 x 255 registers), and the
+// two belong to DIFFERENT systems (the first ctas_per_sys CTAs of the grid are system 0, the rest system 1): while one
+// system's CTA waits for its all-reduce the other's computes, the warp schedulers interleave them for free.  Each
+// system is its own reduction group (own accumulators, counters and partial-sum tables, `Grp`), so the two CG solves
+// of a launch are independent: different iteration counts, no lockstep; only the launch begins and ends together.
+// A row keeps its first P_JR blocks in registers as before; the rest of the row (SELL columns P_JR.. of its slice)
+// lives in shared memory, component-major per warp (conflict-free 8-byte loads) -- registers and shared memory of the
+// 148 SMs together hold both 18 MB matrices of BASELINE configs[2].  Same arithmetic per system as the single-solve
+// kernel, but a row is summed by one thread in column order instead of two half rows: the bits of Ap differ in the
+// last place from the single-solve kernel's (tests compare the trajectories, not bits).
+// =================================================================================================
+constexpr int P_JR = 8;          // block columns of a row in registers
+constexpr int P_THREADS = 128;   // one thread per row, four 32-row slices per CTA
+constexpr int P_HALO_BATCH = 4;  // foreign halo nodes per thread: one round of loads covers 512 per CTA
+constexpr size_t P_PARTIAL_STRIDE = 8192;  // doubles of a.partial per group (2 parities x F_REPLICAS x 3 x <= 160 CTAs fit)
+
+#define JF_BLOCK_FMA_TO(z0, z1, z2, vj, STRIDE, px, py, pz) \
+    z0 = fma((vj)[0 * (STRIDE)], px, z0);                    \
+    z0 = fma((vj)[1 * (STRIDE)], py, z0);                    \
+    z0 = fma((vj)[2 * (STRIDE)], pz, z0);                    \
+    z1 = fma((vj)[3 * (STRIDE)], px, z1);                    \
+    z1 = fma((vj)[4 * (STRIDE)], py, z1);                    \
+    z1 = fma((vj)[5 * (STRIDE)], pz, z1);                    \
+    z2 = fma((vj)[6 * (STRIDE)], px, z2);                    \
+    z2 = fma((vj)[7 * (STRIDE)], py, z2);                    \
+    z2 = fma((vj)[8 * (STRIDE)], pz, z2);
+
+__global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ FusedSharedT<1> sh;
+    __shared__ int s_tail[P_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x / a.ctas_per_sys;
+    const int cb = blockIdx.x - s * a.ctas_per_sys;
+    const Grp grp((unsigned)a.ctas_per_sys, (unsigned)cb);
+    // this system's view of the arguments: one system, its own counters, tables and accumulators
+    CgArgs g = a;
+    g.n_sys = 1;
+    g.partial = a.partial + (size_t)s * P_PARTIAL_STRIDE;
+    g.sync_ctr = a.sync_ctr + s * 32;
+    g.acc = a.acc + (size_t)s * 16 * a.acc_stride;
+    g.state = a.state + s;
+    const int W = P_THREADS / 32;
+    const int rloc = threadIdx.x;
+    const long long sl = (long long)cb * W + warp;
+    const bool have = sl < a.n_slices;
+    const long long row = sl * 32 + lane;
+    const long long vstride = a.Nf_pad * 4;
+    const int hs = a.hmax, fs = a.fmax;
+    double *hp = (double *)dyn_smem;                 // 3 * hmax: p of the halo nodes (own rows first), component-major
+    double *hr = hp + (size_t)hs * 3;                // 3 * fmax: r of the FOREIGN halo nodes
+    double *mt = hr + (size_t)fs * 3;                // tail_max * 288: blocks P_JR.. of the CTA's slices, per warp: [column][component][lane]
+    int *hn = (int *)(mt + (size_t)a.tail_max * 288);   // fmax: node ids of the foreign halo nodes
+    unsigned short *lct = (unsigned short *)(hn + fs);  // tail_max * 32: local columns of the tail blocks
+    const int n_own = min(W, (int)max(0ll, a.n_slices - (long long)cb * W)) * 32;
+    const int h0 = a.halo_ptr[cb], nh = a.halo_ptr[cb + 1] - h0;
+    const int nf = nh - n_own;
+    unsigned epoch = 0;
+
+    if (threadIdx.x == 0) {
+        sh.done[0] = g.state[0].active ? 0 : 1;
+        sh.iters[0] = 0;
+        sh.alpha[0] = 0.0;
+        sh.beta[0] = 0.0;
+        sh.expo_ok[0] = sh.expo_ok[1] = sh.fallback = 0;
+    }
+    for (int i = threadIdx.x; i < 3 * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
+    int w = 0, q0 = 0;
+    if (have) {
+        q0 = a.slice_ptr[sl];
+        w = (a.slice_ptr[sl + 1] - q0) >> 5;
+    }
+    const int wt = max(w - P_JR, 0);  // block columns of this warp's slice that live in shared memory
+    if (lane == 0) s_tail[warp] = wt;
+    __syncthreads();
+    const bool sys_on = !sh.done[0];
+    int toff = 0;
+    for (int k = 0; k < warp; k++) toff += s_tail[k];
+    double *mtw = mt + (size_t)toff * 288 + lane;
+    unsigned short *lctw = lct + toff * 32 + lane;
+
+    double m[P_JR][9];
+    int lc[P_JR];
+#pragma unroll
+    for (int jj = 0; jj < P_JR; jj++) {
+        lc[jj] = 0;
+#pragma unroll
+        for (int q = 0; q < 9; q++) m[jj][q] = 0.0;
+    }
+    if (have && sys_on) {
+        const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288 + lane;
+#pragma unroll
+        for (int jj = 0; jj < P_JR; jj++) {
+            if (jj < w) {
+                lc[jj] = a.lcol[q0 + jj * 32 + lane];
+#pragma unroll
+                for (int q = 0; q < 9; q++) m[jj][q] = v[288 * jj + 32 * q];
+            }
+        }
+        for (int t = 0; t < wt; t++) {
+            lctw[t * 32] = a.lcol[q0 + (P_JR + t) * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < 9; q++) mtw[t * 288 + q * 32] = v[288 * (P_JR + t) + 32 * q];
+        }
+    }
+    for (int h = threadIdx.x; h < nf; h += blockDim.x) hn[h] = a.halo_nodes[h0 + n_own + h];
+    __syncthreads();
+
+    double4 *const A_0 = (double4 *)(a.Ap + s * vstride), *const A_1 = (double4 *)(a.Ap1 + s * vstride);
+    const long long tag_base = (long long)a.launch_seq << 32;
+    auto tag_of = [&](long long iter) { return __longlong_as_double(tag_base | (long long)(unsigned)iter); };
+    if (sys_on) {
+        const double4 *b4 = (const double4 *)(a.b + s * vstride);
+        for (int h = threadIdx.x; h < nf; h += blockDim.x) {
+            const double4 bv = b4[hn[h]];
+            hr[h] = bv.x; hr[fs + h] = bv.y; hr[2 * fs + h] = bv.z;
+            hp[n_own + h] = 0.0; hp[hs + n_own + h] = 0.0; hp[2 * hs + n_own + h] = 0.0;
+        }
+    }
+    double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, y0 = 0, y1 = 0, y2 = 0;
+    double acc = 0.0;
+    if (have && sys_on) {
+        const double4 bv = ((const double4 *)(a.b + s * vstride))[row];
+        r0 = bv.x; r1 = bv.y; r2 = bv.z;
+        st_node(A_1 + row, 0.0, 0.0, 0.0, tag_of(0));  // generation "-1": Ap = 0 makes iteration 0 the general case
+        acc = r0 * r0 + r1 * r1 + r2 * r2;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.warp[0][0][warp] = acc;
+    fused_allreduce<1, 5>(g, grid, sh, epoch, [&](int, double t0, double, double) {
+        sh.normb[0] = t0;
+        sh.rho[0] = t0;
+        sh.tot0[0] = t0;
+        if (!sh.done[0] && t0 == 0.0) sh.done[0] = 1;  // cg returns 0 when normb == 0
+    }, grp);
+
+#ifdef JF_CG_TIMING
+    long long tacc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
+    int cur = 0;
+    unsigned light_target = 0, xe = 0;
+    FxPrev fx_prev;
+    for (long long it = 1; it <= a.maxiter; it++) {
+        if (sh.done[0]) break;
+        FMARK(0);
+        const double alpha = sh.alpha[0], beta = sh.beta[0];  // of the previous iteration (0, 0 for the first)
+        const double4 *Ao = cur ? A_0 : A_1;  // Ap of the previous iteration
+        double4 *An = cur ? A_1 : A_0;        // this iteration's
+        const long long expect = tag_base | (long long)(unsigned)(it - 1);
+        // ---- own row: the deferred updates of the previous iteration ------------------------------------------------
+        if (have) {
+            x0 = fma(alpha, p0, x0);
+            x1 = fma(alpha, p1, x1);
+            x2 = fma(alpha, p2, x2);
+            r0 = fma(-alpha, y0, r0);
+            r1 = fma(-alpha, y1, r1);
+            r2 = fma(-alpha, y2, r2);
+            p0 = fma(beta, p0, r0);
+            p1 = fma(beta, p1, r1);
+            p2 = fma(beta, p2, r2);
+            hp[rloc] = p0;
+            hp[hs + rloc] = p1;
+            hp[2 * hs + rloc] = p2;
+        }
+        // ---- foreign halo: r_j -= alpha Ap_j ; p_j = r_j + beta p_j, r and p kept here
+        {
+            double4 pre[P_HALO_BATCH];
+            int hh[P_HALO_BATCH];
+#pragma unroll
+            for (int k = 0; k < P_HALO_BATCH; k++) {
+                const int h = (int)threadIdx.x + k * P_THREADS;
+                hh[k] = h < nf ? h : 0;
+                pre[k] = ld_node_l2(Ao + hn[hh[k]]);  // (not requested ahead of the all-reduce as in the single-solve kernel: the
+                                                      //  registers hold the matrix, and the SM's other CTA fills the wait)
+            }
+#pragma unroll
+            for (int k = 0; k < P_HALO_BATCH; k++) {  // one node at a time: few temporaries beside the matrix registers
+                if ((int)threadIdx.x + k * P_THREADS < nf) {
+                    while (__double_as_longlong(pre[k].w) != expect) {  // not there yet (rare): read again
+                        pre[k] = ld_node_l2(Ao + hn[hh[k]]);
+#ifdef JF_CG_TIMING
+                        if (threadIdx.x == 32) tacc[12]++;
+#endif
+                    }
+                    const int h = hh[k];
+                    const double q0r = fma(-alpha, pre[k].x, hr[h]), q1r = fma(-alpha, pre[k].y, hr[fs + h]),
+                                 q2r = fma(-alpha, pre[k].z, hr[2 * fs + h]);
+                    const double q0p = hp[n_own + h], q1p = hp[hs + n_own + h], q2p = hp[2 * hs + n_own + h];
+                    hr[h] = q0r;
+                    hr[fs + h] = q1r;
+                    hr[2 * fs + h] = q2r;
+                    hp[n_own + h] = fma(beta, q0p, q0r);
+                    hp[hs + n_own + h] = fma(beta, q1p, q1r);
+                    hp[2 * hs + n_own + h] = fma(beta, q2p, q2r);
+                }
+            }
+        }
+        FMARK(1);
+        __syncthreads();
+        // ---- block row: Ap_i = sum_j K_ij p_j -- registers first, then the tail of the slice from shared memory -------
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        if (have) {
+            y0 = y1 = y2 = 0.0;
+            double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < P_JR; jj += 2) {
+                const double *pa = hp + lc[jj], *pb = hp + lc[jj + 1];
+                const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
+                const double bx = pb[0], by = pb[hs], bz = pb[2 * hs];
+                JF_BLOCK_FMA_TO(y0, y1, y2, m[jj], 1, ax, ay, az)
+                JF_BLOCK_FMA_TO(z0, z1, z2, m[jj + 1], 1, bx, by, bz)
+            }
+            int t = 0;
+            for (; t + 1 < wt; t += 2) {
+                const double *pa = hp + lctw[t * 32], *pb = hp + lctw[(t + 1) * 32];
+                const double *ma = mtw + t * 288, *mb = ma + 288;
+                const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
+                const double bx = pb[0], by = pb[hs], bz = pb[2 * hs];
+                JF_BLOCK_FMA_TO(y0, y1, y2, ma, 32, ax, ay, az)
+                JF_BLOCK_FMA_TO(z0, z1, z2, mb, 32, bx, by, bz)
+            }
+            if (t < wt) {
+                const double *pa = hp + lctw[t * 32];
+                const double *ma = mtw + t * 288;
+                const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
+                JF_BLOCK_FMA_TO(y0, y1, y2, ma, 32, ax, ay, az)
+            }
+            y0 += z0;
+            y1 += z1;
+            y2 += z2;
+            st_node(An + row, y0, y1, y2, tag_of(it));  // ONE 32-byte store: row and tag arrive together
+            a0 = p0 * y0 + p1 * y1 + p2 * y2;
+            a1 = r0 * y0 + r1 * y1 + r2 * y2;
+            a2 = y0 * y0 + y1 * y1 + y2 * y2;
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) {
+            sh.warp[0][0][warp] = a0;
+            sh.warp[1][0][warp] = a1;
+            sh.warp[2][0][warp] = a2;
+        }
+        FMARK(2);
+        auto update = [&](int ss, double pAp, double rAp, double ApAp, int ln) {
+            fused_update_scalars(sh, ss, pAp, rAp, ApAp, ln, it, a.maxiter, a.tol, true, 0);
+        };
+        auto prefetch_halo = [] {};
+        if (sh.expo_ok[0] && sh.expo_ok[1]) {  // the same decision in every CTA of the group: it comes from shared totals
+            fused_fx_allreduce<5, true>(g, sh, epoch, xe, fx_prev, light_target, false, it, true, 0, update, prefetch_halo, grp FT_PASS);
+        } else {
+            const SlotCounters sc = fused_slot_allreduce<5>(g, &sh, epoch, light_target, it, true, 0, grp);
+            epoch = sc.epoch;
+            light_target = sc.light_target;
+            FMARK(7);
+        }
+        cur ^= 1;
+    }
+#ifdef JF_CG_TIMING
+    if (threadIdx.x == 32 && sys_on) {
+        const double n = sh.iters[0] > 0 ? sh.iters[0] : 1;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("cgp sys %d cta %d sm %u nf %d iters %d | top %.0f halo %.0f spmv %.0f | sync_a %.0f words %.0f redpoll %.0f arrive %.0f decode %.0f update %.0f sync_b %.0f | polls %.2f retries %.3f\n",
+               s, cb, smid, nf, sh.iters[0], tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[5] / n, tacc[6] / n,
+               tacc[10] / n, tacc[11] / n, tacc[8] / n, tacc[7] / n, tacc[9] / n, tacc[12] / n);
+    }
+#endif
+    // the last iteration's x += alpha p, then (A12) U[free] += step * x ; du = step^2 * sum x^2
+    acc = 0.0;
+    if (have && g.state[0].active) {
+        const double alpha = sh.alpha[0];
+        x0 = fma(alpha, p0, x0);
+        x1 = fma(alpha, p1, x1);
+        x2 = fma(alpha, p2, x2);
+        ((double4 *)(a.x + s * vstride))[row] = make_double4(x0, x1, x2, 0.0);
+        if (a.apply_update && row < a.Nf) {
+            double *U = a.U + ((long long)s * a.N + row) * 3;
+            U[0] += a.step * x0;
+            U[1] += a.step * x1;
+            U[2] += a.step * x2;
+            acc = x0 * x0 + x1 * x1 + x2 * x2;
+        }
+    }
+    if (a.apply_update) {
+        acc = warp_sum(acc);
+        if (lane == 0) sh.warp[0][0][warp] = acc;
+        fused_allreduce<1, 5>(g, grid, sh, epoch, [&](int, double t0, double, double) { sh.tot0[0] = t0; }, grp);
+    }
+    if (cb == 0 && threadIdx.x == 0 && g.state[0].active) {
+        g.state[0].cg_iters = sh.iters[0];
+        g.state[0].normb = sh.normb[0];
+        g.state[0].resid = sh.rho[0];
+        if (a.apply_update) g.state[0].du = a.step * a.step * sh.tot0[0];
     }
 }
 
@@ -884,7 +1200,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
             long long tacc[14], tlast = 0;
 #endif
             // rows of r, p and Ap cross CTAs here and carry no tag: always the fenced ordering
-            fused_fx_allreduce<10>(a, sh, epoch, xe, fx_prev, light_target, true, it, a.n_sys == 1, cur, update, [] {} FT_PASS);
+            fused_fx_allreduce<10>(a, sh, epoch, xe, fx_prev, light_target, true, it, a.n_sys == 1, cur, update, [] {}, Grp() FT_PASS);
         } else {
             const SlotCounters sc = fused_slot_allreduce<10>(a, &sh, epoch, light_target, it, a.n_sys == 1, cur);
             epoch = sc.epoch;
@@ -948,6 +1264,110 @@ int jf_cg_fused_configure(jf_ctx *c) {
     c->cg_fused_smem = smem;
     c->cg_fused = 1;
     return 1;
+}
+
+// Two systems side by side (jf_cg_pair_kernel): contexts of exactly two systems whose rows fit four slices per CTA with
+// one CTA group of <= 160 CTAs per system and two CTAs per SM -- the sweeps' case on config-2-size meshes.  Builds the
+// kernel's own per-CTA halo lists (own rows first, then the sorted foreign block columns; the streaming kernels of the
+// same context keep theirs).  Returns 1 (configured), 0 (does not apply) or a negative status.
+int jf_cg_pair_configure(jf_ctx *c) {
+    c->cg_pair = 0;
+    if (c->n_sys != 2 || c->n_slices < 1 || getenv("JF_CG_NO_PAIR") || getenv("JF_CG_CLASSIC") || getenv("JF_CG_CGSYNC") ||
+        getenv("JF_CG_SLOT_SUMS") || (c->flags & JF_FLAG_NO_RESIDENT))
+        return 0;
+    const int W = P_THREADS / 32;
+    const int64_t ctas = (c->n_slices + W - 1) / W;
+    if (ctas > 160 || 2 * ctas > 2 * (int64_t)c->sm_count) return 0;  // the collect keeps five partial sums per lane; two CTAs per SM
+    std::vector<int32_t> hptr((size_t)ctas + 1, 0), hnodes;
+    std::vector<uint16_t> lcol((size_t)c->n_slots, 0);
+    std::vector<std::vector<int32_t>> lists((size_t)ctas);
+    std::vector<int> tails((size_t)ctas, 0);
+    jf_parallel_for(ctas, [&](int64_t lo, int64_t hi) {
+        for (int64_t cb = lo; cb < hi; cb++) {
+            const int64_t s0 = cb * W, s1 = std::min<int64_t>(c->n_slices, s0 + W);
+            const int64_t q0 = c->h_slice_ptr[s0], q1 = c->h_slice_ptr[s1];
+            const int32_t own0 = (int32_t)(s0 * JF_SLICE), own1 = (int32_t)(s1 * JF_SLICE);
+            std::vector<int32_t> &foreign = lists[cb];
+            for (int64_t q = q0; q < q1; q++) {
+                const int32_t col = c->h_sell_col[q];
+                if (col < own0 || col >= own1) foreign.push_back(col);
+            }
+            std::sort(foreign.begin(), foreign.end());
+            foreign.erase(std::unique(foreign.begin(), foreign.end()), foreign.end());
+            const int32_t n_own = own1 - own0;
+            for (int64_t q = q0; q < q1; q++) {
+                const int32_t col = c->h_sell_col[q];
+                lcol[q] = (col >= own0 && col < own1)
+                              ? (uint16_t)(col - own0)
+                              : (uint16_t)(n_own + (std::lower_bound(foreign.begin(), foreign.end(), col) - foreign.begin()));
+            }
+            int tail = 0;
+            for (int64_t sl = s0; sl < s1; sl++) tail += std::max(0, (c->h_slice_ptr[sl + 1] - c->h_slice_ptr[sl]) / JF_SLICE - P_JR);
+            tails[cb] = tail;
+        }
+    }, 8);
+    int fmax = 1, tail_max = 1;
+    for (int64_t cb = 0; cb < ctas; cb++) {
+        const int32_t own0 = (int32_t)(cb * W * JF_SLICE), own1 = (int32_t)(std::min<int64_t>(c->n_slices, (cb + 1) * W) * JF_SLICE);
+        for (int32_t i = own0; i < own1; i++) hnodes.push_back(i);
+        hnodes.insert(hnodes.end(), lists[cb].begin(), lists[cb].end());
+        hptr[cb + 1] = (int32_t)hnodes.size();
+        fmax = std::max(fmax, (int)lists[cb].size());
+        tail_max = std::max(tail_max, tails[cb]);
+    }
+    if (fmax > P_HALO_BATCH * P_THREADS) return 0;  // one round of halo loads per thread
+    const int hmax = W * JF_SLICE + fmax;
+    const size_t smem = (size_t)hmax * 3 * sizeof(double) + (size_t)fmax * (3 * sizeof(double) + sizeof(int)) +
+                        (size_t)tail_max * (288 * sizeof(double) + 32 * sizeof(unsigned short));
+    if (cudaFuncSetAttribute(jf_cg_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_pair_kernel, P_THREADS, smem));
+    if ((int64_t)per_sm * c->sm_count < 2 * ctas) return 0;  // both systems co-resident (two CTAs per SM)
+    int rc;
+    if ((rc = jf_dev_alloc(c, &c->d_pair_halo_ptr, hptr.size()))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_pair_halo_nodes, hnodes.size()))) return rc;
+    if ((rc = jf_dev_alloc(c, &c->d_pair_lcol, lcol.size()))) return rc;
+    JF_CUDA(cudaMemcpy(c->d_pair_halo_ptr, hptr.data(), hptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    JF_CUDA(cudaMemcpy(c->d_pair_halo_nodes, hnodes.data(), hnodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    JF_CUDA(cudaMemcpy(c->d_pair_lcol, lcol.data(), lcol.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    c->stats.bytes_h2d += (int64_t)(hptr.size() * 4 + hnodes.size() * 4 + lcol.size() * 2);
+    c->cg_pair = 1;
+    c->cg_pair_ctas = (int)ctas;
+    c->cg_pair_smem = smem;
+    c->cg_pair_hmax = hmax;
+    c->cg_pair_fmax = fmax;
+    c->cg_pair_tail = tail_max;
+    return 1;
+}
+
+int jf_cg_pair_launch(jf_ctx *c, CgArgs &a) {
+    a.prefetch = 1;
+    a.fenced = 0;
+    a.acquire = 0;
+    a.launch_seq = (int)(++c->cg_launch_seq & 0x7fffffff);
+    a.light_barrier = 1;
+    a.exact_sums = 1;
+    a.fx_test = 0;
+    // accumulators of the two groups (16 words each) at the start of d_acc, their barrier counters 512 bytes in
+    a.acc_stride = 1;
+    a.acc = c->d_acc;
+    a.sync_ctr = (unsigned *)(c->d_acc + 64);
+    JF_CUDA(cudaMemsetAsync(c->d_acc, 0, 1024, c->stream));
+    a.halo_ptr = c->d_pair_halo_ptr;
+    a.halo_nodes = c->d_pair_halo_nodes;
+    a.lcol = c->d_pair_lcol;
+    a.hmax = c->cg_pair_hmax;
+    a.fmax = c->cg_pair_fmax;
+    a.tail_max = c->cg_pair_tail;
+    a.ctas_per_sys = c->cg_pair_ctas;
+    a.Ap1 = c->d_Ap1;
+    void *args[] = {&a};
+    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_pair_kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS), args, c->cg_pair_smem,
+                                        c->stream));
+    return 0;
 }
 
 // streaming counterpart: needs the group halo lists of the halo-staged streaming kernel (cg_stream_halo)

@@ -147,7 +147,12 @@ struct jf_ctx {
     int cg_stream_halo = 0, elem_lanes = JF_ELEM_LANES;
     int elem_variant = 0;  // JF_ELEM_VARIANT: unroll / occupancy experiments of the element kernel (4 lanes)
     int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0, cg_hmax = 0, cg_ctas_per_sys = 0;
-    int cg_foreign_max = 0;  // most foreign halo nodes of any CTA (resident kernels)
+    int cg_foreign_max = 0;
+    // two systems side by side (jf_cg_pair_kernel, jf_cg_fused.cu)
+    int cg_pair = 0, cg_pair_ctas = 0, cg_pair_hmax = 0, cg_pair_fmax = 0, cg_pair_tail = 0;
+    size_t cg_pair_smem = 0;
+    int32_t *d_pair_halo_ptr = nullptr, *d_pair_halo_nodes = nullptr;
+    uint16_t *d_pair_lcol = nullptr;  // most foreign halo nodes of any CTA (resident kernels)
     int32_t *d_halo_ptr = nullptr, *d_halo_nodes = nullptr;
     // radial curve extraction (jf_curves.cu)
     int32_t *d_bin_ptr = nullptr, *d_bin_nodes = nullptr;

@@ -116,8 +116,8 @@ class _Claimer:
 
 class SweepEngine:
     """One mesh, one set of displacement conditions, one material on one GPU; load cases (target-force fields) are
-    relaxed one after another through persistent contexts -- one at a time where the register/shared-memory
-    resident CG kernels apply (fastest there), in lockstep batches otherwise (grid barriers amortised)."""
+    relaxed one after another through persistent contexts -- one or two at a time where the register/shared-memory
+    resident CG kernels apply, in lockstep batches otherwise (grid barriers amortised)."""
 
     def __init__(self, coords, tets, bc_displacement, material, step, max_iter, conv_crit, device=0, batch=None, beams=None,
                  curve_bins=None, initial_displacements=None):
@@ -138,8 +138,17 @@ class SweepEngine:
         ctx = self._context(1)
         if batch:
             self.batch = max(1, min(int(batch), 64))
+        elif ctx.info()["cg_resident"]:
+            # matrix on chip: one load case at a time -- or two side by side where the pair kernel applies (two CTAs per
+            # SM, one system each, independent CG solves in one launch: info cg_fused == 4)
+            self.batch = 1
+            if not os.environ.get("JF_CG_NO_PAIR"):
+                if self._context(2).info()["cg_fused"] == 4:
+                    self.batch = 2
+                else:
+                    self.contexts.pop(2).close()
         else:
-            self.batch = 1 if ctx.info()["cg_resident"] else MAX_BATCH
+            self.batch = MAX_BATCH
 
     def _context(self, size):
         if size not in self.contexts:
@@ -176,7 +185,8 @@ class SweepEngine:
         return out
 
     def info(self):
-        return self._context(1).info()
+        """Library info of the context the engine relaxes full batches with."""
+        return self._context(self.batch).info()
 
     def close(self):
         for ctx in self.contexts.values():

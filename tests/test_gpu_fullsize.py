@@ -164,3 +164,67 @@ def test_fullsize_relaxation_matches_oracle_fixture(name, beams, capsys):
     ok = ~np.isnan(g["curve"])
     assert np.array_equal(np.isnan(curve), ~ok)
     assert np.max(np.abs(curve[ok] / g["curve"][ok] - 1)) < 1e-3
+
+
+def test_two_load_cases_side_by_side_match_their_oracle_fixtures(beams, capsys):
+    """The sweeps' kernel on the configs[2] mesh: a context of TWO systems runs both CG solves in one launch, two CTAs
+    per SM, each system its own reduction group (jf_cg_pair_kernel, info cg_fused == 4).  Rows A and B of the
+    lookup-table sweep (different pressures: 95 and 53 Newton steps, different CG iteration counts in every step)
+    relaxed together must each match their own oracle fixture exactly as the single solves do."""
+    from jointforces_b200 import _lib
+    from jointforces_b200.simulation import radial_median_curve, lookup_bins
+    paths = [os.path.join(GOLDEN, "oracle_full_cfg3_row%s.npz" % r) for r in "AB"]
+    if not all(os.path.exists(p) for p in paths):
+        pytest.skip("fixture missing")
+    gs = [np.load(p) for p in paths]
+    cases = [_full_case(g) for g in gs]
+    coords, tets, movable, _ = cases[0]
+    with _lib.Context(coords, tets, movable, n_sys=2, beams=beams) as ctx:
+        info = ctx.info()
+        assert info["cg_fused"] == 4, info
+        ctx.set_material(*gs[0]["material"])
+        for s, c in enumerate(cases):
+            ctx.set_targets(c[3], s)
+            ctx.set_displacements(np.zeros_like(coords), s)
+        relrec, cgit, n = ctx.relax(float(gs[0]["step"]), int(gs[0]["max_iter"]), 0.01)
+        U = [ctx.displacements(s) for s in range(2)]
+        st = ctx.stats()
+    x, _ = lookup_bins()
+    for s, g in enumerate(gs):
+        assert int(n[s]) == len(g["relrec"]) - 1
+        stride = int(g["stride"])
+        err = np.linalg.norm(U[s][::stride] - g["U_sub"]) / np.linalg.norm(g["U_sub"])
+        d = cgit[s][:int(n[s])].astype(np.int64) - g["cg_iters"]
+        with capsys.disabled():
+            print("\n[pair, system %d] %d Newton steps, CG iterations %d vs oracle %d: signed mean difference %+.2f per step, "
+                  "|U-U_oracle|/|U_oracle| = %.2e" % (s, n[s], cgit[s].sum(), g["cg_iters"].sum(), d.mean(), err))
+        assert err < 1e-4, err
+        assert np.allclose(relrec[s][:int(n[s]) + 1, 1], g["relrec"][:, 1], rtol=1e-4)
+        assert -0.05 <= d.sum() / g["cg_iters"].sum() <= 0.01
+        curve = radial_median_curve(coords, U[s], 100e-6, x)
+        ok = ~np.isnan(g["curve"])
+        assert np.max(np.abs(curve[ok] / g["curve"][ok] - 1)) < 1e-3
+    with capsys.disabled():
+        print("[pair] device time %.1f ms for both (CG %.1f ms, %d iterations in total)" % (st["ms_relax"], st["ms_cg"], st["cg_iterations"]))
+
+
+def test_pair_kernel_is_bitwise_reproducible_and_independent_of_its_neighbour(beams):
+    """Integer-accumulated sums and per-system reduction groups: a system's trajectory does not depend on what the other
+    system of the launch is doing, nor on the run."""
+    from jointforces_b200 import _lib
+    g = np.load(os.path.join(GOLDEN, "oracle_full_cfg3_rowA.npz"))
+    coords, tets, movable, ft = _full_case(g)
+    out = []
+    with _lib.Context(coords, tets, movable, n_sys=2, beams=beams) as ctx:
+        assert ctx.info()["cg_fused"] == 4
+        ctx.set_material(*g["material"])
+        for other in (1.0, 37.0, 37.0):
+            ctx.set_targets(ft, 0)
+            ctx.set_targets(ft * other, 1)
+            for s in range(2):
+                ctx.set_displacements(np.zeros_like(coords), s)
+            relrec, cgit, n = ctx.relax(float(g["step"]), 12, 0.01)
+            out.append((ctx.displacements(0), cgit[0].copy(), ctx.displacements(1)))
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])   # neighbour changed: same bits
+    assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][2], out[2][2])   # same run twice: same bits
+    assert np.array_equal(out[0][0], out[0][2])                                            # same load case in both slots: same bits
