@@ -746,7 +746,13 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
 // =================================================================================================
 constexpr int P_JR = 8;          // block columns of a row in registers
 constexpr int P_THREADS = 128;   // one thread per row, four 32-row slices per CTA
-constexpr int P_HALO_BATCH = 4;  // foreign halo nodes per thread: one round of loads covers 512 per CTA
+constexpr int P_HALO_BATCH = 4;  // foreign halo nodes per row thread: one round of loads covers 512 per CTA
+#ifndef P_DEFAULT_LANES
+#define P_DEFAULT_LANES 1
+#endif
+#ifndef P_PREFETCH
+#define P_PREFETCH 2
+#endif
 constexpr size_t P_PARTIAL_STRIDE = 8192;  // doubles of a.partial per group (2 parities x F_REPLICAS x 3 x <= 160 CTAs fit)
 
 #define JF_BLOCK_FMA_TO(z0, z1, z2, vj, STRIDE, px, py, pz) \
@@ -760,7 +766,14 @@ constexpr size_t P_PARTIAL_STRIDE = 8192;  // doubles of a.partial per group (2 
     z2 = fma((vj)[7 * (STRIDE)], py, z2);                    \
     z2 = fma((vj)[8 * (STRIDE)], pz, z2);
 
-__global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
+// LANES = threads per block row: 1 (128 threads, 255 registers: a row's P_JR register blocks in one thread) or 2 (256 threads,
+// 128 registers: two warps per slice, lane half h takes the SELL columns j with j % 2 == h as in jf_cg_fused_kernel,
+// P_JR / 2 of them in registers; twice the warps to hide the latencies of a phase, the same shared-memory traffic).
+template <int LANES>
+__global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs a) {
+    constexpr int NT = P_THREADS * LANES;      // threads per CTA
+    constexpr int JR = P_JR / LANES;           // register blocks per thread
+    constexpr int HB = P_HALO_BATCH / LANES;   // foreign halo nodes per thread
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ FusedSharedT<1> sh;
@@ -776,16 +789,19 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
     g.sync_ctr = a.sync_ctr + s * 32;
     g.acc = a.acc + (size_t)s * 16 * a.acc_stride;
     g.state = a.state + s;
-    const int W = P_THREADS / 32;
-    const int rloc = threadIdx.x;
-    const long long sl = (long long)cb * W + warp;
+    const int W = P_THREADS / 32;  // slices per CTA
+    const int half = LANES == 2 ? lane >> 4 : 0;
+    const int rloc = LANES == 2 ? warp * 16 + (lane & 15) : (int)threadIdx.x;  // local row
+    const int rl = rloc & 31;                                                  // row within its slice
+    const long long sl = (long long)cb * W + (rloc >> 5);
     const bool have = sl < a.n_slices;
-    const long long row = sl * 32 + lane;
+    const bool owner = have && half == 0;
+    const long long row = sl * 32 + rl;
     const long long vstride = a.Nf_pad * 4;
     const int hs = a.hmax, fs = a.fmax;
     double *hp = (double *)dyn_smem;                 // 3 * hmax: p of the halo nodes (own rows first), component-major
     double *hr = hp + (size_t)hs * 3;                // 3 * fmax: r of the FOREIGN halo nodes
-    double *mt = hr + (size_t)fs * 3;                // tail_max * 288: blocks P_JR.. of the CTA's slices, per warp: [column][component][lane]
+    double *mt = hr + (size_t)fs * 3;                // tail_max * 288: blocks P_JR.. of the CTA's slices, per slice: [column][component][row]
     int *hn = (int *)(mt + (size_t)a.tail_max * 288);   // fmax: node ids of the foreign halo nodes
     unsigned short *lct = (unsigned short *)(hn + fs);  // tail_max * 32: local columns of the tail blocks
     const int n_own = min(W, (int)max(0ll, a.n_slices - (long long)cb * W)) * 32;
@@ -800,46 +816,47 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
         sh.beta[0] = 0.0;
         sh.expo_ok[0] = sh.expo_ok[1] = sh.fallback = 0;
     }
-    for (int i = threadIdx.x; i < 3 * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
+    for (int i = threadIdx.x; i < 3 * 8; i += NT) (&sh.warp[0][0][0])[i] = 0.0;
     int w = 0, q0 = 0;
     if (have) {
         q0 = a.slice_ptr[sl];
         w = (a.slice_ptr[sl + 1] - q0) >> 5;
     }
-    const int wt = max(w - P_JR, 0);  // block columns of this warp's slice that live in shared memory
-    if (lane == 0) s_tail[warp] = wt;
+    const int wt = max(w - P_JR, 0);  // block columns of this row's slice that live in shared memory
+    if (rl == 0 && half == 0) s_tail[rloc >> 5] = wt;
     __syncthreads();
     const bool sys_on = !sh.done[0];
     int toff = 0;
-    for (int k = 0; k < warp; k++) toff += s_tail[k];
-    double *mtw = mt + (size_t)toff * 288 + lane;
-    unsigned short *lctw = lct + toff * 32 + lane;
+    for (int k = 0; k < (rloc >> 5); k++) toff += s_tail[k];
+    double *mtw = mt + (size_t)toff * 288 + rl;
+    unsigned short *lctw = lct + toff * 32 + rl;
 
-    double m[P_JR][9];
-    int lc[P_JR];
+    double m[JR][9];
+    int lc[JR];
 #pragma unroll
-    for (int jj = 0; jj < P_JR; jj++) {
+    for (int jj = 0; jj < JR; jj++) {
         lc[jj] = 0;
 #pragma unroll
         for (int q = 0; q < 9; q++) m[jj][q] = 0.0;
     }
     if (have && sys_on) {
-        const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288 + lane;
+        const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288 + rl;
 #pragma unroll
-        for (int jj = 0; jj < P_JR; jj++) {
-            if (jj < w) {
-                lc[jj] = a.lcol[q0 + jj * 32 + lane];
+        for (int jj = 0; jj < JR; jj++) {
+            const int j = LANES * jj + half;
+            if (j < w) {
+                lc[jj] = a.lcol[q0 + j * 32 + rl];
 #pragma unroll
-                for (int q = 0; q < 9; q++) m[jj][q] = v[288 * jj + 32 * q];
+                for (int q = 0; q < 9; q++) m[jj][q] = v[288 * j + 32 * q];
             }
         }
-        for (int t = 0; t < wt; t++) {
-            lctw[t * 32] = a.lcol[q0 + (P_JR + t) * 32 + lane];
+        for (int t = half; t < wt; t += LANES) {
+            lctw[t * 32] = a.lcol[q0 + (P_JR + t) * 32 + rl];
 #pragma unroll
             for (int q = 0; q < 9; q++) mtw[t * 288 + q * 32] = v[288 * (P_JR + t) + 32 * q];
         }
     }
-    for (int h = threadIdx.x; h < nf; h += blockDim.x) hn[h] = a.halo_nodes[h0 + n_own + h];
+    for (int h = threadIdx.x; h < nf; h += NT) hn[h] = a.halo_nodes[h0 + n_own + h];
     __syncthreads();
 
     double4 *const A_0 = (double4 *)(a.Ap + s * vstride), *const A_1 = (double4 *)(a.Ap1 + s * vstride);
@@ -847,7 +864,7 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
     auto tag_of = [&](long long iter) { return __longlong_as_double(tag_base | (long long)(unsigned)iter); };
     if (sys_on) {
         const double4 *b4 = (const double4 *)(a.b + s * vstride);
-        for (int h = threadIdx.x; h < nf; h += blockDim.x) {
+        for (int h = threadIdx.x; h < nf; h += NT) {
             const double4 bv = b4[hn[h]];
             hr[h] = bv.x; hr[fs + h] = bv.y; hr[2 * fs + h] = bv.z;
             hp[n_own + h] = 0.0; hp[hs + n_own + h] = 0.0; hp[2 * hs + n_own + h] = 0.0;
@@ -858,8 +875,10 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
     if (have && sys_on) {
         const double4 bv = ((const double4 *)(a.b + s * vstride))[row];
         r0 = bv.x; r1 = bv.y; r2 = bv.z;
-        st_node(A_1 + row, 0.0, 0.0, 0.0, tag_of(0));  // generation "-1": Ap = 0 makes iteration 0 the general case
-        acc = r0 * r0 + r1 * r1 + r2 * r2;
+        if (owner) {
+            st_node(A_1 + row, 0.0, 0.0, 0.0, tag_of(0));  // generation "-1": Ap = 0 makes iteration 0 the general case
+            acc = r0 * r0 + r1 * r1 + r2 * r2;
+        }
     }
     acc = warp_sum(acc);
     if (lane == 0) sh.warp[0][0][warp] = acc;
@@ -876,6 +895,13 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
     int cur = 0;
     unsigned light_target = 0, xe = 0;
     FxPrev fx_prev;
+    // PREFETCH (LANES == 1): the foreign Ap rows of the next iteration are requested before the all-reduce's poll, as in the
+    // single-solve kernel -- one L2 round trip less on the CTA's critical path (the period of a lone CTA, not the SM's
+    // throughput, bounds the pair: tools/pair_probe.py); with two lanes per row there are no registers for it
+    constexpr int NPRE = LANES == 1 ? P_PREFETCH : 0;  // of a thread's HB foreign nodes, how many are requested ahead
+    double4 pre[HB];
+#pragma unroll
+    for (int k = 0; k < HB; k++) pre[k] = make_double4(0.0, 0.0, 0.0, tag_of(0));
     for (long long it = 1; it <= a.maxiter; it++) {
         if (sh.done[0]) break;
         FMARK(0);
@@ -883,35 +909,35 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
         const double4 *Ao = cur ? A_0 : A_1;  // Ap of the previous iteration
         double4 *An = cur ? A_1 : A_0;        // this iteration's
         const long long expect = tag_base | (long long)(unsigned)(it - 1);
-        // ---- own row: the deferred updates of the previous iteration ------------------------------------------------
-        if (have) {
-            x0 = fma(alpha, p0, x0);
-            x1 = fma(alpha, p1, x1);
-            x2 = fma(alpha, p2, x2);
-            r0 = fma(-alpha, y0, r0);
-            r1 = fma(-alpha, y1, r1);
-            r2 = fma(-alpha, y2, r2);
-            p0 = fma(beta, p0, r0);
-            p1 = fma(beta, p1, r1);
-            p2 = fma(beta, p2, r2);
-            hp[rloc] = p0;
-            hp[hs + rloc] = p1;
-            hp[2 * hs + rloc] = p2;
-        }
         // ---- foreign halo: r_j -= alpha Ap_j ; p_j = r_j + beta p_j, r and p kept here
         {
-            double4 pre[P_HALO_BATCH];
-            int hh[P_HALO_BATCH];
+            int hh[HB];
 #pragma unroll
-            for (int k = 0; k < P_HALO_BATCH; k++) {
-                const int h = (int)threadIdx.x + k * P_THREADS;
+            for (int k = 0; k < HB; k++) {
+                const int h = (int)threadIdx.x + k * NT;
                 hh[k] = h < nf ? h : 0;
-                pre[k] = ld_node_l2(Ao + hn[hh[k]]);  // (not requested ahead of the all-reduce as in the single-solve kernel: the
-                                                      //  registers hold the matrix, and the SM's other CTA fills the wait)
+                if (k >= NPRE) pre[k] = ld_node_l2(Ao + hn[hh[k]]);
+            }
+            // ---- own row meanwhile: the deferred updates of the previous iteration ---------------------------------
+            if (have) {
+                x0 = fma(alpha, p0, x0);
+                x1 = fma(alpha, p1, x1);
+                x2 = fma(alpha, p2, x2);
+                r0 = fma(-alpha, y0, r0);
+                r1 = fma(-alpha, y1, r1);
+                r2 = fma(-alpha, y2, r2);
+                p0 = fma(beta, p0, r0);
+                p1 = fma(beta, p1, r1);
+                p2 = fma(beta, p2, r2);
+                if (half == 0) {
+                    hp[rloc] = p0;
+                    hp[hs + rloc] = p1;
+                    hp[2 * hs + rloc] = p2;
+                }
             }
 #pragma unroll
-            for (int k = 0; k < P_HALO_BATCH; k++) {  // one node at a time: few temporaries beside the matrix registers
-                if ((int)threadIdx.x + k * P_THREADS < nf) {
+            for (int k = 0; k < HB; k++) {  // one node at a time: few temporaries beside the matrix registers
+                if ((int)threadIdx.x + k * NT < nf) {
                     while (__double_as_longlong(pre[k].w) != expect) {  // not there yet (rare): read again
                         pre[k] = ld_node_l2(Ao + hn[hh[k]]);
 #ifdef JF_CG_TIMING
@@ -939,17 +965,17 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
             y0 = y1 = y2 = 0.0;
             double z0 = 0.0, z1 = 0.0, z2 = 0.0;
 #pragma unroll
-            for (int jj = 0; jj < P_JR; jj += 2) {
+            for (int jj = 0; jj < JR; jj += 2) {
                 const double *pa = hp + lc[jj], *pb = hp + lc[jj + 1];
                 const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
                 const double bx = pb[0], by = pb[hs], bz = pb[2 * hs];
                 JF_BLOCK_FMA_TO(y0, y1, y2, m[jj], 1, ax, ay, az)
                 JF_BLOCK_FMA_TO(z0, z1, z2, m[jj + 1], 1, bx, by, bz)
             }
-            int t = 0;
-            for (; t + 1 < wt; t += 2) {
-                const double *pa = hp + lctw[t * 32], *pb = hp + lctw[(t + 1) * 32];
-                const double *ma = mtw + t * 288, *mb = ma + 288;
+            int t = half;
+            for (; t + LANES < wt; t += 2 * LANES) {
+                const double *pa = hp + lctw[t * 32], *pb = hp + lctw[(t + LANES) * 32];
+                const double *ma = mtw + t * 288, *mb = ma + LANES * 288;
                 const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
                 const double bx = pb[0], by = pb[hs], bz = pb[2 * hs];
                 JF_BLOCK_FMA_TO(y0, y1, y2, ma, 32, ax, ay, az)
@@ -964,10 +990,17 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
             y0 += z0;
             y1 += z1;
             y2 += z2;
-            st_node(An + row, y0, y1, y2, tag_of(it));  // ONE 32-byte store: row and tag arrive together
-            a0 = p0 * y0 + p1 * y1 + p2 * y2;
-            a1 = r0 * y0 + r1 * y1 + r2 * y2;
-            a2 = y0 * y0 + y1 * y1 + y2 * y2;
+            if (LANES == 2) {
+                y0 += __shfl_xor_sync(0xffffffffu, y0, 16);
+                y1 += __shfl_xor_sync(0xffffffffu, y1, 16);
+                y2 += __shfl_xor_sync(0xffffffffu, y2, 16);
+            }
+            if (owner) {
+                st_node(An + row, y0, y1, y2, tag_of(it));  // ONE 32-byte store: row and tag arrive together
+                a0 = p0 * y0 + p1 * y1 + p2 * y2;
+                a1 = r0 * y0 + r1 * y1 + r2 * y2;
+                a2 = y0 * y0 + y1 * y1 + y2 * y2;
+            }
         }
         a0 = warp_sum(a0);
         a1 = warp_sum(a1);
@@ -981,13 +1014,21 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
         auto update = [&](int ss, double pAp, double rAp, double ApAp, int ln) {
             fused_update_scalars(sh, ss, pAp, rAp, ApAp, ln, it, a.maxiter, a.tol, true, 0);
         };
-        auto prefetch_halo = [] {};
+        auto request = [&]() {
+            const double4 *An_c = cur ? A_1 : A_0;
+#pragma unroll
+            for (int k = 0; k < NPRE; k++) {
+                const int h = (int)threadIdx.x + k * NT;
+                pre[k] = ld_node_l2(An_c + hn[h < nf ? h : 0]);
+            }
+        };
         if (sh.expo_ok[0] && sh.expo_ok[1]) {  // the same decision in every CTA of the group: it comes from shared totals
-            fused_fx_allreduce<5, true>(g, sh, epoch, xe, fx_prev, light_target, false, it, true, 0, update, prefetch_halo, grp FT_PASS);
+            fused_fx_allreduce<5, true>(g, sh, epoch, xe, fx_prev, light_target, false, it, true, 0, update, request, grp FT_PASS);
         } else {
             const SlotCounters sc = fused_slot_allreduce<5>(g, &sh, epoch, light_target, it, true, 0, grp);
             epoch = sc.epoch;
             light_target = sc.light_target;
+            request();
             FMARK(7);
         }
         cur ^= 1;
@@ -1004,7 +1045,7 @@ __global__ void __launch_bounds__(P_THREADS, 2) jf_cg_pair_kernel(CgArgs a) {
 #endif
     // the last iteration's x += alpha p, then (A12) U[free] += step * x ; du = step^2 * sum x^2
     acc = 0.0;
-    if (have && g.state[0].active) {
+    if (owner && g.state[0].active) {
         const double alpha = sh.alpha[0];
         x0 = fma(alpha, p0, x0);
         x1 = fma(alpha, p1, x1);
@@ -1319,12 +1360,15 @@ int jf_cg_pair_configure(jf_ctx *c) {
     const int hmax = W * JF_SLICE + fmax;
     const size_t smem = (size_t)hmax * 3 * sizeof(double) + (size_t)fmax * (3 * sizeof(double) + sizeof(int)) +
                         (size_t)tail_max * (288 * sizeof(double) + 32 * sizeof(unsigned short));
-    if (cudaFuncSetAttribute(jf_cg_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    const char *lanes_env = getenv("JF_CG_PAIR_LANES");
+    const int lanes = lanes_env ? (atoi(lanes_env) == 2 ? 2 : 1) : P_DEFAULT_LANES;
+    const void *kernel = lanes == 2 ? (const void *)jf_cg_pair_kernel<2> : (const void *)jf_cg_pair_kernel<1>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_pair_kernel, P_THREADS, smem));
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, P_THREADS * lanes, smem));
     if ((int64_t)per_sm * c->sm_count < 2 * ctas) return 0;  // both systems co-resident (two CTAs per SM)
     int rc;
     if ((rc = jf_dev_alloc(c, &c->d_pair_halo_ptr, hptr.size()))) return rc;
@@ -1334,7 +1378,7 @@ int jf_cg_pair_configure(jf_ctx *c) {
     JF_CUDA(cudaMemcpy(c->d_pair_halo_nodes, hnodes.data(), hnodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     JF_CUDA(cudaMemcpy(c->d_pair_lcol, lcol.data(), lcol.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     c->stats.bytes_h2d += (int64_t)(hptr.size() * 4 + hnodes.size() * 4 + lcol.size() * 2);
-    c->cg_pair = 1;
+    c->cg_pair = lanes;
     c->cg_pair_ctas = (int)ctas;
     c->cg_pair_smem = smem;
     c->cg_pair_hmax = hmax;
@@ -1365,8 +1409,8 @@ int jf_cg_pair_launch(jf_ctx *c, CgArgs &a) {
     a.ctas_per_sys = c->cg_pair_ctas;
     a.Ap1 = c->d_Ap1;
     void *args[] = {&a};
-    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_pair_kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS), args, c->cg_pair_smem,
-                                        c->stream));
+    JF_CUDA(cudaLaunchCooperativeKernel(c->cg_pair == 2 ? (void *)jf_cg_pair_kernel<2> : (void *)jf_cg_pair_kernel<1>, dim3(2 * c->cg_pair_ctas),
+                                        dim3(P_THREADS * c->cg_pair), args, c->cg_pair_smem, c->stream));
     return 0;
 }
 
