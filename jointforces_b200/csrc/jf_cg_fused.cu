@@ -753,6 +753,9 @@ constexpr int P_HALO_BATCH = 4;  // foreign halo nodes per row thread: one round
 #ifndef P_PREFETCH
 #define P_PREFETCH 2
 #endif
+#ifndef P_DEFAULT_TMEM
+#define P_DEFAULT_TMEM 0
+#endif
 constexpr size_t P_PARTIAL_STRIDE = 8192;  // doubles of a.partial per group (2 parities x F_REPLICAS x 3 x <= 160 CTAs fit)
 
 #define JF_BLOCK_FMA_TO(z0, z1, z2, vj, STRIDE, px, py, pz) \
@@ -766,11 +769,47 @@ constexpr size_t P_PARTIAL_STRIDE = 8192;  // doubles of a.partial per group (2 
     z2 = fma((vj)[7 * (STRIDE)], py, z2);                    \
     z2 = fma((vj)[8 * (STRIDE)], pz, z2);
 
+
+// ---- tensor memory as plain storage (jf_cg_pair_kernel<1, true>) -----------------------------------------------------
+// TMEM (256 KB per SM, 128 lanes x 512 columns of 32 bits) is idle in a kernel without tensor-core work.  A CTA of four
+// warps owns one lane per thread (warp w may touch lanes 32 (w % 4) ... + 31), so with 256 allocated columns every thread
+// has 1 KB = 128 doubles of private storage that is read by tcgen05.ld straight into registers -- not through the
+// LSU / shared-memory pipe the block rows' p gathers need.  The shared-memory tail of a row lives there instead.
+__device__ __forceinline__ void tmem_st_double(unsigned taddr, double v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+#define TM_R4(r, o) "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3])
+__device__ __forceinline__ void tmem_ld_x2(unsigned taddr, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(unsigned taddr, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : TM_R4(r, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(unsigned taddr, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TM_R4(r, 0), TM_R4(r, 4), TM_R4(r, 8), TM_R4(r, 12)
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(unsigned taddr, unsigned *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : TM_R4(r, 0), TM_R4(r, 4), TM_R4(r, 8), TM_R4(r, 12), TM_R4(r, 16), TM_R4(r, 20), TM_R4(r, 24), TM_R4(r, 28)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+constexpr int TM_COLS = 256;                 // columns per CTA: two CTAs per SM share the 512
+constexpr int TM_MAX_TAIL = TM_COLS / 18;    // block columns of a row that fit (18 words per 3x3 block of doubles)
+
 // LANES = threads per block row: 1 (128 threads, 255 registers: a row's P_JR register blocks in one thread) or 2 (256 threads,
 // 128 registers: two warps per slice, lane half h takes the SELL columns j with j % 2 == h as in jf_cg_fused_kernel,
 // P_JR / 2 of them in registers; twice the warps to hide the latencies of a phase, the same shared-memory traffic).
-template <int LANES>
+// TMEM = the tail of the rows in tensor memory instead of shared memory (one lane per row only).
+template <int LANES, bool TMEM = false>
 __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs a) {
+    static_assert(!TMEM || LANES == 1, "tensor-memory tail: one thread per row");
     constexpr int NT = P_THREADS * LANES;      // threads per CTA
     constexpr int JR = P_JR / LANES;           // register blocks per thread
     constexpr int HB = P_HALO_BATCH / LANES;   // foreign halo nodes per thread
@@ -802,7 +841,7 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
     double *hp = (double *)dyn_smem;                 // 3 * hmax: p of the halo nodes (own rows first), component-major
     double *hr = hp + (size_t)hs * 3;                // 3 * fmax: r of the FOREIGN halo nodes
     double *mt = hr + (size_t)fs * 3;                // tail_max * 288: blocks P_JR.. of the CTA's slices, per slice: [column][component][row]
-    int *hn = (int *)(mt + (size_t)a.tail_max * 288);   // fmax: node ids of the foreign halo nodes
+    int *hn = (int *)(mt + (TMEM ? (size_t)0 : (size_t)a.tail_max * 288));   // fmax: node ids of the foreign halo nodes
     unsigned short *lct = (unsigned short *)(hn + fs);  // tail_max * 32: local columns of the tail blocks
     const int n_own = min(W, (int)max(0ll, a.n_slices - (long long)cb * W)) * 32;
     const int h0 = a.halo_ptr[cb], nh = a.halo_ptr[cb + 1] - h0;
@@ -824,7 +863,19 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
     }
     const int wt = max(w - P_JR, 0);  // block columns of this row's slice that live in shared memory
     if (rl == 0 && half == 0) s_tail[rloc >> 5] = wt;
+    __shared__ unsigned s_tmem;
+    if (TMEM) {
+        if (warp == 0) {  // one warp allocates; the permit is given up at once so that the SM's other CTA can allocate too
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"((unsigned long long)__cvta_generic_to_shared(&s_tmem)),
+                         "n"(TM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
     __syncthreads();
+    if (TMEM) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tm = TMEM ? s_tmem + ((unsigned)((warp & 3) * 32) << 16) : 0u;  // this warp's lanes, column 0
     const bool sys_on = !sh.done[0];
     int toff = 0;
     for (int k = 0; k < (rloc >> 5); k++) toff += s_tail[k];
@@ -852,9 +903,20 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
         }
         for (int t = half; t < wt; t += LANES) {
             lctw[t * 32] = a.lcol[q0 + (P_JR + t) * 32 + rl];
+            if (!TMEM) {
 #pragma unroll
-            for (int q = 0; q < 9; q++) mtw[t * 288 + q * 32] = v[288 * (P_JR + t) + 32 * q];
+                for (int q = 0; q < 9; q++) mtw[t * 288 + q * 32] = v[288 * (P_JR + t) + 32 * q];
+            }
         }
+    }
+    if (TMEM) {  // (warp-collective stores: the slice width is the same for the whole warp)
+        const bool ld = have && sys_on;
+        const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288 + rl;
+        for (int t = 0; t < wt; t++) {
+#pragma unroll
+            for (int q = 0; q < 9; q++) tmem_st_double(tm + t * 18 + 2 * q, ld ? v[288 * (P_JR + t) + 32 * q] : 0.0);
+        }
+        tmem_wait_st();
     }
     for (int h = threadIdx.x; h < nf; h += NT) hn[h] = a.halo_nodes[h0 + n_own + h];
     __syncthreads();
@@ -973,6 +1035,35 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
                 JF_BLOCK_FMA_TO(z0, z1, z2, m[jj + 1], 1, bx, by, bz)
             }
             int t = half;
+            if (TMEM) {
+                for (; t + 1 < wt; t += 2) {  // two blocks = 36 words per tcgen05.ld pair, while the p gathers go through shared memory
+                    unsigned mw[36];
+                    tmem_ld_x32(tm + t * 18, mw);
+                    tmem_ld_x4(tm + t * 18 + 32, mw + 32);
+                    const double *pa = hp + lctw[t * 32], *pb = hp + lctw[(t + 1) * 32];
+                    const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
+                    const double bx = pb[0], by = pb[hs], bz = pb[2 * hs];
+                    tmem_wait_ld();
+                    double md[18];
+#pragma unroll
+                    for (int q = 0; q < 18; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
+                    JF_BLOCK_FMA_TO(y0, y1, y2, md, 1, ax, ay, az)
+                    JF_BLOCK_FMA_TO(z0, z1, z2, (md + 9), 1, bx, by, bz)
+                }
+                if (t < wt) {
+                    unsigned mw[18];
+                    tmem_ld_x16(tm + t * 18, mw);
+                    tmem_ld_x2(tm + t * 18 + 16, mw + 16);
+                    const double *pa = hp + lctw[t * 32];
+                    const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
+                    tmem_wait_ld();
+                    double md[9];
+#pragma unroll
+                    for (int q = 0; q < 9; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
+                    JF_BLOCK_FMA_TO(y0, y1, y2, md, 1, ax, ay, az)
+                }
+                t = wt;
+            }
             for (; t + LANES < wt; t += 2 * LANES) {
                 const double *pa = hp + lctw[t * 32], *pb = hp + lctw[(t + LANES) * 32];
                 const double *ma = mtw + t * 288, *mb = ma + LANES * 288;
@@ -1069,6 +1160,11 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
         g.state[0].normb = sh.normb[0];
         g.state[0].resid = sh.rho[0];
         if (a.apply_update) g.state[0].du = a.step * a.step * sh.tot0[0];
+    }
+    if (TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TM_COLS) : "memory");
     }
 }
 
@@ -1358,11 +1454,16 @@ int jf_cg_pair_configure(jf_ctx *c) {
     }
     if (fmax > P_HALO_BATCH * P_THREADS) return 0;  // one round of halo loads per thread
     const int hmax = W * JF_SLICE + fmax;
-    const size_t smem = (size_t)hmax * 3 * sizeof(double) + (size_t)fmax * (3 * sizeof(double) + sizeof(int)) +
-                        (size_t)tail_max * (288 * sizeof(double) + 32 * sizeof(unsigned short));
+    size_t smem = (size_t)hmax * 3 * sizeof(double) + (size_t)fmax * (3 * sizeof(double) + sizeof(int)) +
+                  (size_t)tail_max * (288 * sizeof(double) + 32 * sizeof(unsigned short));
     const char *lanes_env = getenv("JF_CG_PAIR_LANES");
     const int lanes = lanes_env ? (atoi(lanes_env) == 2 ? 2 : 1) : P_DEFAULT_LANES;
-    const void *kernel = lanes == 2 ? (const void *)jf_cg_pair_kernel<2> : (const void *)jf_cg_pair_kernel<1>;
+    const char *tmem_env = getenv("JF_CG_PAIR_TMEM");
+    bool tmem = lanes == 1 && (tmem_env ? atoi(tmem_env) != 0 : P_DEFAULT_TMEM != 0);
+    if (c->cg_wmax - P_JR > TM_MAX_TAIL) tmem = false;
+    if (tmem) smem -= (size_t)tail_max * 288 * sizeof(double);
+    const void *kernel = tmem ? (const void *)jf_cg_pair_kernel<1, true>
+                              : (lanes == 2 ? (const void *)jf_cg_pair_kernel<2> : (const void *)jf_cg_pair_kernel<1>);
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -1378,7 +1479,7 @@ int jf_cg_pair_configure(jf_ctx *c) {
     JF_CUDA(cudaMemcpy(c->d_pair_halo_nodes, hnodes.data(), hnodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     JF_CUDA(cudaMemcpy(c->d_pair_lcol, lcol.data(), lcol.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     c->stats.bytes_h2d += (int64_t)(hptr.size() * 4 + hnodes.size() * 4 + lcol.size() * 2);
-    c->cg_pair = lanes;
+    c->cg_pair = tmem ? 3 : lanes;  // 1, 2: lanes per row, tail in shared memory; 3: one lane per row, tail in tensor memory
     c->cg_pair_ctas = (int)ctas;
     c->cg_pair_smem = smem;
     c->cg_pair_hmax = hmax;
@@ -1409,8 +1510,9 @@ int jf_cg_pair_launch(jf_ctx *c, CgArgs &a) {
     a.ctas_per_sys = c->cg_pair_ctas;
     a.Ap1 = c->d_Ap1;
     void *args[] = {&a};
-    JF_CUDA(cudaLaunchCooperativeKernel(c->cg_pair == 2 ? (void *)jf_cg_pair_kernel<2> : (void *)jf_cg_pair_kernel<1>, dim3(2 * c->cg_pair_ctas),
-                                        dim3(P_THREADS * c->cg_pair), args, c->cg_pair_smem, c->stream));
+    void *kernel = c->cg_pair == 3 ? (void *)jf_cg_pair_kernel<1, true> : (c->cg_pair == 2 ? (void *)jf_cg_pair_kernel<2> : (void *)jf_cg_pair_kernel<1>);
+    JF_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS * (c->cg_pair == 2 ? 2 : 1)), args, c->cg_pair_smem,
+                                        c->stream));
     return 0;
 }
 
