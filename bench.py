@@ -483,10 +483,10 @@ def main():
             flat, step_of = [], []
             for j in range(j0, j0 + nsteps):
                 idx = step_indices(j)
-                flat += [int(i) for i in idx[np.argsort(-costs_all[idx], kind="stable")]]
+                flat += [int(i) for i in idx[jsweep.work_order(TABLE[idx], costs_all[idx], engine.batch)]]
                 step_of += [j] * len(idx)
             flat = np.asarray(flat)
-            claimer = jsweep._Claimer(np.arange(len(flat)), costs_all[flat], rank, world, "dynamic")
+            claimer = jsweep._Claimer(np.arange(len(flat)), costs_all[flat], rank, world, "dynamic", batch=engine.batch)
             ms, rows, done, last_step = 0.0, [], [], None
             while True:
                 chunk = claimer.take(engine.batch)

@@ -85,11 +85,30 @@ def shard_indices(values, rank, world, material=None):
     return lpt_assignment(pressure_cost(values, material), world)[rank]
 
 
+def work_order(values, costs, batch=1):
+    """The order in which load cases are handed out: most expensive first.  With ``batch`` cases relaxed side by side
+    (lockstep Newton steps, one CG launch for the batch) the members of a batch should follow similar trajectories, or
+    the quicker one idles: batches are runs of ``batch`` NEIGHBOURS ON THE VALUE AXIS (similar pressure -> similar Newton
+    and CG iteration counts; two pressures of equal cost on opposite sides of the cost peak differ by a factor of two in
+    Newton steps), and the batches are ordered by their summed cost, dearest first."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n = len(costs)
+    if batch <= 1 or n <= batch:
+        return np.argsort(-costs, kind="stable")
+    by_value = np.argsort(np.asarray(values, dtype=np.float64), kind="stable")
+    groups = [by_value[a:a + batch] for a in range(0, n, batch)]
+    groups.sort(key=lambda g: -float(costs[g].sum() / len(g)))
+    # a short last group (n not a multiple of batch) goes to the end: every draw before it is a full batch
+    full = [g for g in groups if len(g) == batch]
+    short = [g for g in groups if len(g) < batch]
+    return np.concatenate(full + short)
+
+
 class _Claimer:
     """Hands out positions 0..n-1 of the cost-ordered work list.  With a store: a shared counter (dynamic schedule);
     without: this rank's LPT share."""
 
-    def __init__(self, order, costs, rank, world, schedule):
+    def __init__(self, order, costs, rank, world, schedule, batch=1):
         global _SWEEP_CALLS
         _SWEEP_CALLS += 1
         self.order = order
@@ -98,9 +117,15 @@ class _Claimer:
         if self.store is not None:
             self.key = "jf_b200_sweep_%d" % _SWEEP_CALLS
             self.static = None
+        elif world > 1:
+            # static deal of whole batches (runs of `batch` entries of the order stay together on one rank)
+            chunks = [order[a:a + batch] for a in range(0, self.n, max(1, batch))]
+            chunk_cost = [float(np.sum(np.asarray(costs)[np.asarray(ch, dtype=np.int64)])) for ch in chunks]
+            mine = lpt_assignment(chunk_cost, world)[rank]
+            self.static = [int(i) for k in mine for i in chunks[int(k)]]
+            self.pos = 0
         else:
-            share = set(lpt_assignment(costs, world)[rank].tolist()) if world > 1 else None
-            self.static = [i for i in order if share is None or int(i) in share]
+            self.static = [int(i) for i in order]
             self.pos = 0
 
     def take(self, count):
@@ -265,19 +290,19 @@ def run_sweep(meshfile, outfolder, values, material, var_arg='pressure', max_ite
     # the radius exactly as the table builder recovers it from parameters.txt (simulation.py:296-297)
     r_curve = (r_in * 1e6) * 10 ** -6
     costs = pressure_cost(values, material)
-    order = np.sort(np.arange(len(values))) if warm_start else np.argsort(-costs, kind="stable")
-    claimer = _Claimer(order, costs, rank, world, "lpt" if warm_start else schedule)
+    own = engine is None
+    if own:
+        bc0 = sim.spherical_boundary_conditions(coords, r_in, r_out, float(values[0]) if len(values) else 1.0)
+        engine = SweepEngine(coords, tets, bc0['displacement'], material, step, max_iter, conv_crit, device=device,
+                             batch=1 if warm_start else batch, curve_bins=(r_curve, x))
+    order = np.sort(np.arange(len(values))) if warm_start else work_order(values, costs, engine.batch)
+    claimer = _Claimer(order, costs, rank, world, "lpt" if warm_start else schedule, batch=engine.batch)
     mat_par = SemiAffineFiberMaterial(material['K_0'], material['D_0'], material['L_S'], material['D_S']).serialize()
     tets64 = tets.astype(np.int64)
-    bc0 = sim.spherical_boundary_conditions(coords, r_in, r_out, float(values[0]) if len(values) else 1.0)
-    own = engine is None
     done, curves, ms = [], [], []
     writer = ThreadPoolExecutor(max_workers=2) if write else None
     pending = []
     try:
-        if own:
-            engine = SweepEngine(coords, tets, bc0['displacement'], material, step, max_iter, conv_crit, device=device,
-                                 batch=1 if warm_start else batch, curve_bins=(r_curve, x))
         first = True
         while True:
             chunk = claimer.take(engine.batch)
