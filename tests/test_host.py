@@ -330,6 +330,32 @@ def test_dynamic_work_queue_two_ranks_gloo(tmp_path):
     assert set(first) <= set(np.argsort(-cost, kind="stable")[:3].tolist())   # the dearest cases go out first
 
 
+def test_work_order_keeps_neighbouring_pressures_together():
+    """Batches relaxed side by side are runs of neighbours on the pressure axis (similar Newton / CG iteration counts), the
+    dearest batch first; a batch size of one is plain cost order; every case appears exactly once; the static deal keeps
+    batches on one rank."""
+    values = np.logspace(-1, 4, 150)
+    cost = sweep.pressure_cost(values)
+    assert np.array_equal(sweep.work_order(values, cost, 1), np.argsort(-cost, kind="stable"))
+    order = sweep.work_order(values, cost, 2)
+    assert sorted(order.tolist()) == list(range(150))
+    pairs = order.reshape(-1, 2)
+    assert np.all(np.abs(pairs[:, 0] - pairs[:, 1]) == 1)                 # neighbours in the (sorted) value list
+    pair_cost = cost[pairs].sum(1)
+    assert np.all(np.diff(pair_cost) <= 1e-12)                            # dearest first
+    shuffled = np.random.default_rng(1).permutation(150)
+    o2 = sweep.work_order(values[shuffled], cost[shuffled], 2).reshape(-1, 2)
+    assert np.all(np.abs(np.log10(values[shuffled][o2[:, 0]] / values[shuffled][o2[:, 1]])) < 0.04)   # unsorted input: still neighbours
+    odd = sweep.work_order(values[:7], cost[:7], 2)
+    assert sorted(odd.tolist()) == list(range(7)) and len(odd) == 7
+    for rank in range(3):                                                 # static deal (no process group): whole batches per rank
+        c = sweep._Claimer(order, cost, rank, 3, "lpt", batch=2)
+        mine = np.asarray(c.static).reshape(-1, 2)
+        assert np.all(np.abs(mine[:, 0] - mine[:, 1]) == 1)
+    dealt = sorted(i for rank in range(3) for i in sweep._Claimer(order, cost, rank, 3, "lpt", batch=2).static)
+    assert dealt == list(range(150))
+
+
 def _gloo_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
