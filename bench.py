@@ -160,7 +160,8 @@ def roofline_of(info, st, peaks, peak_kind, workload):
     by_iter = cg_bytes_per_iteration(info)
     achieved = by_iter * st["cg_iterations"] / (st["ms_cg"] * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "cg_traffic_%s.json" % ("cfg2" if workload == "cfg3" else workload))
+    tname = "cfg3_pair" if info.get("cg_fused") == 4 else ("cfg2" if workload == "cfg3" else workload)
+    tpath = os.path.join(ROOT, "profiles", "cg_traffic_%s.json" % tname)
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")

@@ -806,12 +806,15 @@ constexpr int TM_MAX_TAIL = TM_COLS / 18;    // block columns of a row that fit 
 // LANES = threads per block row: 1 (128 threads, 255 registers: a row's P_JR register blocks in one thread) or 2 (256 threads,
 // 128 registers: two warps per slice, lane half h takes the SELL columns j with j % 2 == h as in jf_cg_fused_kernel,
 // P_JR / 2 of them in registers; twice the warps to hide the latencies of a phase, the same shared-memory traffic).
-// TMEM = the tail of the rows in tensor memory instead of shared memory (one lane per row only).
+// TMEM = the tail of the rows in tensor memory instead of shared memory.  With one lane per row the first P_JR columns stay
+// in registers; with two lanes per row (128 registers per thread) only the first four do -- two per thread -- and up to
+// seven more per thread live in the thread's 128 tensor-memory columns (warps w and w + 4 share a lane quarter and take
+// one half of the 256 columns each).
 template <int LANES, bool TMEM = false>
 __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs a) {
-    static_assert(!TMEM || LANES == 1, "tensor-memory tail: one thread per row");
     constexpr int NT = P_THREADS * LANES;      // threads per CTA
-    constexpr int JR = P_JR / LANES;           // register blocks per thread
+    constexpr int RJ = (TMEM && LANES == 2) ? 4 : P_JR;  // SELL columns of a row that live in registers
+    constexpr int JR = RJ / LANES;             // register blocks per thread
     constexpr int HB = P_HALO_BATCH / LANES;   // foreign halo nodes per thread
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -861,7 +864,8 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
         q0 = a.slice_ptr[sl];
         w = (a.slice_ptr[sl + 1] - q0) >> 5;
     }
-    const int wt = max(w - P_JR, 0);  // block columns of this row's slice that live in shared memory
+    const int wt = max(w - RJ, 0);  // block columns of this row's slice that live in shared / tensor memory
+    const int wtu = (wt + LANES - 1) / LANES;  // ... per thread (tensor memory: the same trip count for both lane halves)
     if (rl == 0 && half == 0) s_tail[rloc >> 5] = wt;
     __shared__ unsigned s_tmem;
     if (TMEM) {
@@ -875,7 +879,9 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
     }
     __syncthreads();
     if (TMEM) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tm = TMEM ? s_tmem + ((unsigned)((warp & 3) * 32) << 16) : 0u;  // this warp's lanes, column 0
+    // this warp's lanes; warps 4..7 (two lanes per row) use the upper half of the columns
+    const unsigned tm = TMEM ? s_tmem + ((unsigned)((warp & 3) * 32) << 16) + (warp >= 4 ? TM_COLS / 2 : 0) : 0u;
+    unsigned short *lctt = lct + threadIdx.x;  // tensor-memory tail: local columns per thread, [t][NT]
     const bool sys_on = !sh.done[0];
     int toff = 0;
     for (int k = 0; k < (rloc >> 5); k++) toff += s_tail[k];
@@ -901,20 +907,22 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
                 for (int q = 0; q < 9; q++) m[jj][q] = v[288 * j + 32 * q];
             }
         }
-        for (int t = half; t < wt; t += LANES) {
-            lctw[t * 32] = a.lcol[q0 + (P_JR + t) * 32 + rl];
-            if (!TMEM) {
+        if (!TMEM) {
+            for (int t = half; t < wt; t += LANES) {
+                lctw[t * 32] = a.lcol[q0 + (RJ + t) * 32 + rl];
 #pragma unroll
-                for (int q = 0; q < 9; q++) mtw[t * 288 + q * 32] = v[288 * (P_JR + t) + 32 * q];
+                for (int q = 0; q < 9; q++) mtw[t * 288 + q * 32] = v[288 * (RJ + t) + 32 * q];
             }
         }
     }
-    if (TMEM) {  // (warp-collective stores: the slice width is the same for the whole warp)
-        const bool ld = have && sys_on;
+    if (TMEM) {  // (warp-collective stores: the slice width is the same for the whole warp; a lane half without a block stores zeros)
         const double *v = a.val + (long long)s * a.n_slots * 9 + (long long)(q0 >> 5) * 288 + rl;
-        for (int t = 0; t < wt; t++) {
+        for (int t = 0; t < wtu; t++) {
+            const int j = RJ + LANES * t + half;
+            const bool ld = have && sys_on && j < w;
+            lctt[t * NT] = ld ? a.lcol[q0 + j * 32 + rl] : (unsigned short)0;
 #pragma unroll
-            for (int q = 0; q < 9; q++) tmem_st_double(tm + t * 18 + 2 * q, ld ? v[288 * (P_JR + t) + 32 * q] : 0.0);
+            for (int q = 0; q < 9; q++) tmem_st_double(tm + t * 18 + 2 * q, ld ? v[288 * j + 32 * q] : 0.0);
         }
         tmem_wait_st();
     }
@@ -1036,31 +1044,38 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
             }
             int t = half;
             if (TMEM) {
-                for (; t + 1 < wt; t += 2) {  // two blocks = 36 words per tcgen05.ld pair, while the p gathers go through shared memory
-                    unsigned mw[36];
-                    tmem_ld_x32(tm + t * 18, mw);
-                    tmem_ld_x4(tm + t * 18 + 32, mw + 32);
-                    const double *pa = hp + lctw[t * 32], *pb = hp + lctw[(t + 1) * 32];
-                    const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
-                    const double bx = pb[0], by = pb[hs], bz = pb[2 * hs];
-                    tmem_wait_ld();
-                    double md[18];
+                int u = 0;
+                if (LANES == 1) {
+                    for (; u + 1 < wtu; u += 2) {  // two blocks = 36 words per tcgen05.ld pair, while the p gathers go through shared memory
+                        unsigned mw[36];
+                        tmem_ld_x32(tm + u * 18, mw);
+                        tmem_ld_x4(tm + u * 18 + 32, mw + 32);
+                        const double *pa = hp + lctt[u * NT], *pb = hp + lctt[(u + 1) * NT];
+                        const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
+                        const double bx = pb[0], by = pb[hs], bz = pb[2 * hs];
+                        tmem_wait_ld();
+                        double md[18];
 #pragma unroll
-                    for (int q = 0; q < 18; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
-                    JF_BLOCK_FMA_TO(y0, y1, y2, md, 1, ax, ay, az)
-                    JF_BLOCK_FMA_TO(z0, z1, z2, (md + 9), 1, bx, by, bz)
+                        for (int q = 0; q < 18; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
+                        JF_BLOCK_FMA_TO(y0, y1, y2, md, 1, ax, ay, az)
+                        JF_BLOCK_FMA_TO(z0, z1, z2, (md + 9), 1, bx, by, bz)
+                    }
                 }
-                if (t < wt) {
+                for (; u < wtu; u++) {
                     unsigned mw[18];
-                    tmem_ld_x16(tm + t * 18, mw);
-                    tmem_ld_x2(tm + t * 18 + 16, mw + 16);
-                    const double *pa = hp + lctw[t * 32];
+                    tmem_ld_x16(tm + u * 18, mw);
+                    tmem_ld_x2(tm + u * 18 + 16, mw + 16);
+                    const double *pa = hp + lctt[u * NT];
                     const double ax = pa[0], ay = pa[hs], az = pa[2 * hs];
                     tmem_wait_ld();
                     double md[9];
 #pragma unroll
                     for (int q = 0; q < 9; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
-                    JF_BLOCK_FMA_TO(y0, y1, y2, md, 1, ax, ay, az)
+                    if (u & 1) {
+                        JF_BLOCK_FMA_TO(z0, z1, z2, md, 1, ax, ay, az)
+                    } else {
+                        JF_BLOCK_FMA_TO(y0, y1, y2, md, 1, ax, ay, az)
+                    }
                 }
                 t = wt;
             }
@@ -1459,10 +1474,14 @@ int jf_cg_pair_configure(jf_ctx *c) {
     const char *lanes_env = getenv("JF_CG_PAIR_LANES");
     const int lanes = lanes_env ? (atoi(lanes_env) == 2 ? 2 : 1) : P_DEFAULT_LANES;
     const char *tmem_env = getenv("JF_CG_PAIR_TMEM");
-    bool tmem = lanes == 1 && (tmem_env ? atoi(tmem_env) != 0 : P_DEFAULT_TMEM != 0);
-    if (c->cg_wmax - P_JR > TM_MAX_TAIL) tmem = false;
-    if (tmem) smem -= (size_t)tail_max * 288 * sizeof(double);
-    const void *kernel = tmem ? (const void *)jf_cg_pair_kernel<1, true>
+    bool tmem = tmem_env ? atoi(tmem_env) != 0 : P_DEFAULT_TMEM != 0;
+    // columns of a row beyond the register blocks, per thread: at most what its tensor-memory columns hold
+    const int tm_tail = lanes == 2 ? (c->cg_wmax - 4 + 1) / 2 : c->cg_wmax - P_JR;
+    if (tm_tail > (lanes == 2 ? TM_MAX_TAIL / 2 : TM_MAX_TAIL)) tmem = false;
+    if (tmem)  // no matrix tail in shared memory; the tail's local columns per thread instead of per slice
+        smem = (size_t)hmax * 3 * sizeof(double) + (size_t)fmax * (3 * sizeof(double) + sizeof(int)) +
+               (size_t)std::max(tm_tail, 1) * P_THREADS * lanes * sizeof(unsigned short);
+    const void *kernel = tmem ? (lanes == 2 ? (const void *)jf_cg_pair_kernel<2, true> : (const void *)jf_cg_pair_kernel<1, true>)
                               : (lanes == 2 ? (const void *)jf_cg_pair_kernel<2> : (const void *)jf_cg_pair_kernel<1>);
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
@@ -1479,7 +1498,7 @@ int jf_cg_pair_configure(jf_ctx *c) {
     JF_CUDA(cudaMemcpy(c->d_pair_halo_nodes, hnodes.data(), hnodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     JF_CUDA(cudaMemcpy(c->d_pair_lcol, lcol.data(), lcol.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     c->stats.bytes_h2d += (int64_t)(hptr.size() * 4 + hnodes.size() * 4 + lcol.size() * 2);
-    c->cg_pair = tmem ? 3 : lanes;  // 1, 2: lanes per row, tail in shared memory; 3: one lane per row, tail in tensor memory
+    c->cg_pair = lanes + (tmem ? 2 : 0);  // 1, 2: lanes per row, tail in shared memory; 3, 4: the same with the tail in tensor memory
     c->cg_pair_ctas = (int)ctas;
     c->cg_pair_smem = smem;
     c->cg_pair_hmax = hmax;
@@ -1510,9 +1529,12 @@ int jf_cg_pair_launch(jf_ctx *c, CgArgs &a) {
     a.ctas_per_sys = c->cg_pair_ctas;
     a.Ap1 = c->d_Ap1;
     void *args[] = {&a};
-    void *kernel = c->cg_pair == 3 ? (void *)jf_cg_pair_kernel<1, true> : (c->cg_pair == 2 ? (void *)jf_cg_pair_kernel<2> : (void *)jf_cg_pair_kernel<1>);
-    JF_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS * (c->cg_pair == 2 ? 2 : 1)), args, c->cg_pair_smem,
-                                        c->stream));
+    void *kernel = c->cg_pair == 4   ? (void *)jf_cg_pair_kernel<2, true>
+                   : c->cg_pair == 3 ? (void *)jf_cg_pair_kernel<1, true>
+                   : c->cg_pair == 2 ? (void *)jf_cg_pair_kernel<2>
+                                     : (void *)jf_cg_pair_kernel<1>;
+    const int lanes = (c->cg_pair - 1) % 2 + 1;
+    JF_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS * lanes), args, c->cg_pair_smem, c->stream));
     return 0;
 }
 
