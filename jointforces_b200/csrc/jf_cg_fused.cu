@@ -22,6 +22,7 @@
 // one 256-bit load per halo node per iteration; two generations alternate by parity.
 //
 // Measured on config 2: 6.4-6.8 us per iteration with two barriers -> see DESIGN.md / profiles.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -50,6 +51,10 @@ constexpr int F_HALO_BATCH = 2;  // one round of loads covers 512 foreign halo n
 #ifndef JF_ACC_DEFAULT_STRIDE
 #define JF_ACC_DEFAULT_STRIDE 1
 #endif
+// polls of a grid-wide wait before the kernel gives up (tens of seconds): the spin barriers need every CTA of the group
+// resident, which a cooperative launch guarantees; jf_cg_pair_kernel with its tail in tensor memory is launched plainly
+// (the occupancy calculator grants kernels that allocate tensor memory one CTA per SM, the hardware runs two)
+constexpr unsigned JF_SPIN_LIMIT = 1u << 25;
 constexpr int F_MAX_SYS = 16;   // systems per launch in this kernel (shared tables are sized by it)
 
 template <int MS>
@@ -87,9 +92,10 @@ __device__ __forceinline__ void light_grid_barrier(unsigned *ctr, unsigned &targ
         target += n_ctas;
         __threadfence();  // (red.release.gpu compiles to the same MEMBAR + REDG sequence)
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-        unsigned seen;
+        unsigned seen, spins = 0;
         do {  // relaxed poll; what is read from other CTAs afterwards comes from L2 (ld.global.cg), see fused_fx_allreduce
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+            if (++spins > JF_SPIN_LIMIT) __trap();  // a CTA of the group is not resident (cannot happen under a cooperative launch)
         } while (seen < target);
     }
     __syncthreads();
@@ -350,7 +356,9 @@ __device__ __forceinline__ void fused_fx_allreduce(const CgArgs &a, SH &sh, unsi
         if (lane < 7) asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + lane * a.acc_stride), "l"(wd) : "memory");
         if (!fenced) request();
         bool complete;
+        unsigned spins = 0;
         do {
+            if (++spins > JF_SPIN_LIMIT) __trap();
             if (lane < 7) {
                 // (acquire = LDG.STRONG.GPU + CCTL.IVALL: an L1 invalidation per poll, which costs the streaming kernel 13 % --
                 //  it keeps its index arrays in L1; everything read from other CTAs afterwards is loaded with ld.global.cg,
@@ -754,7 +762,7 @@ constexpr int P_HALO_BATCH = 4;  // foreign halo nodes per row thread: one round
 #define P_PREFETCH 2
 #endif
 #ifndef P_DEFAULT_TMEM
-#define P_DEFAULT_TMEM 0
+#define P_DEFAULT_TMEM 1
 #endif
 constexpr size_t P_PARTIAL_STRIDE = 8192;  // doubles of a.partial per group (2 parities x F_REPLICAS x 3 x <= 160 CTAs fit)
 
@@ -952,18 +960,23 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
     }
     acc = warp_sum(acc);
     if (lane == 0) sh.warp[0][0][warp] = acc;
-    fused_allreduce<1, 5>(g, grid, sh, epoch, [&](int, double t0, double, double) {
-        sh.normb[0] = t0;
-        sh.rho[0] = t0;
-        sh.tot0[0] = t0;
-        if (!sh.done[0] && t0 == 0.0) sh.done[0] = 1;  // cg returns 0 when normb == 0
-    }, grp);
+    unsigned light_target = 0, xe = 0;
+    // (group-local counter barriers also at the two ends of the solve: the kernel never needs the whole grid, so its
+    //  tensor-memory variants can be launched without the cooperative-launch occupancy check)
+    {
+        const double *part = fused_publish_sync<1, true>(g, grid, sh, epoch, &light_target, grp);
+        fused_collect<1, 5>(g, sh, part, [&](int, double t0, double, double) {
+            sh.normb[0] = t0;
+            sh.rho[0] = t0;
+            sh.tot0[0] = t0;
+            if (!sh.done[0] && t0 == 0.0) sh.done[0] = 1;  // cg returns 0 when normb == 0
+        }, grp);
+    }
 
 #ifdef JF_CG_TIMING
     long long tacc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
     int cur = 0;
-    unsigned light_target = 0, xe = 0;
     FxPrev fx_prev;
     // PREFETCH (LANES == 1): the foreign Ap rows of the next iteration are requested before the all-reduce's poll, as in the
     // single-solve kernel -- one L2 round trip less on the CTA's critical path (the period of a lone CTA, not the SM's
@@ -1168,7 +1181,8 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
     if (a.apply_update) {
         acc = warp_sum(acc);
         if (lane == 0) sh.warp[0][0][warp] = acc;
-        fused_allreduce<1, 5>(g, grid, sh, epoch, [&](int, double t0, double, double) { sh.tot0[0] = t0; }, grp);
+        const double *part = fused_publish_sync<1, true>(g, grid, sh, epoch, &light_target, grp);
+        fused_collect<1, 5>(g, sh, part, [&](int, double t0, double, double) { sh.tot0[0] = t0; }, grp);
     }
     if (cb == 0 && threadIdx.x == 0 && g.state[0].active) {
         g.state[0].cg_iters = sh.iters[0];
@@ -1483,12 +1497,25 @@ int jf_cg_pair_configure(jf_ctx *c) {
                (size_t)std::max(tm_tail, 1) * P_THREADS * lanes * sizeof(unsigned short);
     const void *kernel = tmem ? (lanes == 2 ? (const void *)jf_cg_pair_kernel<2, true> : (const void *)jf_cg_pair_kernel<1, true>)
                               : (lanes == 2 ? (const void *)jf_cg_pair_kernel<2> : (const void *)jf_cg_pair_kernel<1>);
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    const bool verbose = getenv("JF_TIMING") != nullptr;
+    cudaError_t fe = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (fe != cudaSuccess) {
+        if (verbose) fprintf(stderr, "jf_cg_pair_configure: cudaFuncSetAttribute(%zu bytes): %s\n", smem, cudaGetErrorString(fe));
         cudaGetLastError();
         return 0;
     }
     int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, P_THREADS * lanes, smem));
+    // (the calculator answers 1 for any kernel that allocates tensor memory; registers and shared memory are what limit
+    //  these kernels, so the twin without tensor memory is asked with the same launch shape)
+    const void *twin = lanes == 2 ? (const void *)jf_cg_pair_kernel<2> : (const void *)jf_cg_pair_kernel<1>;
+    if (tmem && cudaFuncSetAttribute(twin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tmem ? twin : kernel, P_THREADS * lanes, smem));
+    if (verbose)
+        fprintf(stderr, "jf_cg_pair_configure: lanes %d tmem %d, %lld CTAs per system, %zu bytes of shared memory, %d CTAs per SM\n", lanes, (int)tmem,
+                (long long)ctas, smem, per_sm);
     if ((int64_t)per_sm * c->sm_count < 2 * ctas) return 0;  // both systems co-resident (two CTAs per SM)
     int rc;
     if ((rc = jf_dev_alloc(c, &c->d_pair_halo_ptr, hptr.size()))) return rc;
@@ -1534,7 +1561,10 @@ int jf_cg_pair_launch(jf_ctx *c, CgArgs &a) {
                    : c->cg_pair == 2 ? (void *)jf_cg_pair_kernel<2>
                                      : (void *)jf_cg_pair_kernel<1>;
     const int lanes = (c->cg_pair - 1) % 2 + 1;
-    JF_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS * lanes), args, c->cg_pair_smem, c->stream));
+    if (c->cg_pair >= 3)  // tensor memory: plain launch (see JF_SPIN_LIMIT); 2 * ctas <= two CTAs per SM was checked at configure time
+        JF_CUDA(cudaLaunchKernel(kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS * lanes), args, c->cg_pair_smem, c->stream));
+    else
+        JF_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(2 * c->cg_pair_ctas), dim3(P_THREADS * lanes), args, c->cg_pair_smem, c->stream));
     return 0;
 }
 
