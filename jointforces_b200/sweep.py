@@ -113,6 +113,7 @@ class _Claimer:
         _SWEEP_CALLS += 1
         self.order = order
         self.n = len(order)
+        self.world = world
         self.store = _group_store() if schedule == "dynamic" else None
         if self.store is not None:
             self.key = "jf_b200_sweep_%d" % _SWEEP_CALLS
@@ -129,8 +130,13 @@ class _Claimer:
             self.pos = 0
 
     def take(self, count):
-        """Up to ``count`` load-case indices, [] when the list is exhausted."""
+        """Up to ``count`` load-case indices, [] when the list is exhausted.  Near the end of a shared list the draws
+        shrink to single cases: a batch drawn by one rank while the others have nothing left would be the whole tail."""
         if self.store is not None:
+            if count > 1 and self.world > 1:
+                taken = int(self.store.add(self.key, 0))
+                if self.n - taken <= self.world * count:
+                    count = 1
             end = int(self.store.add(self.key, count))
             start = end - count
             return [int(i) for i in self.order[start:min(end, self.n)]] if start < self.n else []
