@@ -171,8 +171,8 @@ def roofline_of(info, st, peaks, peak_kind, workload):
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
             "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": by_iter * st["cg_iterations"] / max(1, st["cg_launches"]),
             "us_per_cg_iteration": st["ms_cg"] * 1e3 / max(1, st["cg_iterations"]),
-            "achieved_is": ("a rate of algorithmic bytes: the %.0f MB matrix of a system is staged once per CG solve into registers / "
-                            "shared memory, DRAM is idle (`traffic`); the iteration is bound by its grid-wide all-reduce%s. "
+            "achieved_is": ("a rate of algorithmic bytes: the %.0f MB matrix of a system is staged once per CG solve into registers and "
+                            "tensor / shared memory, DRAM is idle (`traffic`); the iteration is bound by its grid-wide all-reduce%s. "
                             "roofline_large is the HBM-bound regime"
                             % (matrix_mb, " (two systems per launch, two CTAs per SM: us_per_cg_iteration is per system-iteration)"
                                if info.get("cg_fused") == 4 else "")) if resident else "HBM traffic (matrix streamed)"}

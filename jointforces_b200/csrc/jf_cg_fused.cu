@@ -752,7 +752,10 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
 // kernel, but a row is summed by one thread in column order instead of two half rows: the bits of Ap differ in the
 // last place from the single-solve kernel's (tests compare the trajectories, not bits).
 // =================================================================================================
-constexpr int P_JR = 8;          // block columns of a row in registers
+#ifndef P_JR_REGS
+#define P_JR_REGS 8
+#endif
+constexpr int P_JR = P_JR_REGS;  // block columns of a row in registers
 constexpr int P_THREADS = 128;   // one thread per row, four 32-row slices per CTA
 constexpr int P_HALO_BATCH = 4;  // foreign halo nodes per row thread: one round of loads covers 512 per CTA
 #ifndef P_DEFAULT_LANES
