@@ -755,7 +755,13 @@ __global__ void __launch_bounds__(256, 1) jf_cg_fused_kernel(CgArgs a) {
 #ifndef P_JR_REGS
 #define P_JR_REGS 8
 #endif
-constexpr int P_JR = P_JR_REGS;  // block columns of a row in registers
+#ifndef P_JR_TMEM_REGS
+#define P_JR_TMEM_REGS 4
+#endif
+constexpr int P_JR = P_JR_REGS;  // block columns of a row in registers (tail in shared memory)
+// ... with the tail in tensor memory: a block there costs what a register block costs (the p gathers set both), and
+// four register blocks leave the kernel without spills: 8 / 6 / 4 in registers: 3.74 / 3.53 / 3.51 us per pair of iterations
+constexpr int P_JR_TMEM = P_JR_TMEM_REGS;
 constexpr int P_THREADS = 128;   // one thread per row, four 32-row slices per CTA
 constexpr int P_HALO_BATCH = 4;  // foreign halo nodes per row thread: one round of loads covers 512 per CTA
 #ifndef P_DEFAULT_LANES
@@ -817,14 +823,14 @@ constexpr int TM_MAX_TAIL = TM_COLS / 18;    // block columns of a row that fit 
 // LANES = threads per block row: 1 (128 threads, 255 registers: a row's P_JR register blocks in one thread) or 2 (256 threads,
 // 128 registers: two warps per slice, lane half h takes the SELL columns j with j % 2 == h as in jf_cg_fused_kernel,
 // P_JR / 2 of them in registers; twice the warps to hide the latencies of a phase, the same shared-memory traffic).
-// TMEM = the tail of the rows in tensor memory instead of shared memory.  With one lane per row the first P_JR columns stay
+// TMEM = the tail of the rows in tensor memory instead of shared memory.  With one lane per row the first P_JR_TMEM columns stay
 // in registers; with two lanes per row (128 registers per thread) only the first four do -- two per thread -- and up to
 // seven more per thread live in the thread's 128 tensor-memory columns (warps w and w + 4 share a lane quarter and take
 // one half of the 256 columns each).
 template <int LANES, bool TMEM = false>
 __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs a) {
     constexpr int NT = P_THREADS * LANES;      // threads per CTA
-    constexpr int RJ = (TMEM && LANES == 2) ? 4 : P_JR;  // SELL columns of a row that live in registers
+    constexpr int RJ = TMEM ? (LANES == 2 ? 4 : P_JR_TMEM) : P_JR;  // SELL columns of a row that live in registers
     constexpr int JR = RJ / LANES;             // register blocks per thread
     constexpr int HB = P_HALO_BATCH / LANES;   // foreign halo nodes per thread
     cg::grid_group grid = cg::this_grid();
@@ -1493,7 +1499,7 @@ int jf_cg_pair_configure(jf_ctx *c) {
     const char *tmem_env = getenv("JF_CG_PAIR_TMEM");
     bool tmem = tmem_env ? atoi(tmem_env) != 0 : P_DEFAULT_TMEM != 0;
     // columns of a row beyond the register blocks, per thread: at most what its tensor-memory columns hold
-    const int tm_tail = lanes == 2 ? (c->cg_wmax - 4 + 1) / 2 : c->cg_wmax - P_JR;
+    const int tm_tail = lanes == 2 ? (c->cg_wmax - 4 + 1) / 2 : c->cg_wmax - P_JR_TMEM;
     if (tm_tail > (lanes == 2 ? TM_MAX_TAIL / 2 : TM_MAX_TAIL)) tmem = false;
     if (tmem)  // no matrix tail in shared memory; the tail's local columns per thread instead of per slice
         smem = (size_t)hmax * 3 * sizeof(double) + (size_t)fmax * (3 * sizeof(double) + sizeof(int)) +
