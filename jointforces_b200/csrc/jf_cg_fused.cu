@@ -1213,13 +1213,24 @@ __global__ void __launch_bounds__(P_THREADS * LANES, 2) jf_cg_pair_kernel(CgArgs
 // shared memory for the group's block-row products; the owner pass advances x, r, p of its rows and publishes
 // the new generation.  One grid barrier per iteration instead of two and no separate vector-update pass.
 // =================================================================================================
+#ifndef FS_DEFAULT_TMEM
+#define FS_DEFAULT_TMEM 1
+#endif
 constexpr int FS_SLICES = 8;
 constexpr int FS_THREADS = FS_SLICES * 32;
 
+// TMEM = a CTA keeps the first FS_TM_BLOCKS block columns of its FIRST group of slices in tensor memory for the whole solve
+// (one system only): with one group per CTA -- BASELINE configs[3]: 300 groups on 296 CTAs -- that is 7 of the ~15 blocks of
+// every row that no longer stream from L2 in every iteration (84 MB matrix: 39 MB in tensor memory, 45 MB streamed).
+// Plain launch, group barriers at both ends and the spin watchdog as for jf_cg_pair_kernel.
+constexpr int FS_TM_BLOCKS = (TM_COLS / 2) / 18;  // warps w and w + 4 share a lane quarter: 128 columns = 7 blocks per thread
+
+template <bool TMEM>
 __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double hv[];  // hmax * 3
     __shared__ FusedShared sh;
+    __shared__ unsigned s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const long long wg = (long long)warp * gridDim.x + blockIdx.x;
     const long long nwg = (long long)gridDim.x * nwarps;
@@ -1236,7 +1247,33 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
     }
     if (threadIdx.x == 0) sh.expo_ok[0] = sh.expo_ok[1] = sh.fallback = 0;
     for (int i = threadIdx.x; i < 3 * F_MAX_SYS * 8; i += blockDim.x) (&sh.warp[0][0][0])[i] = 0.0;
+    if (TMEM) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"((unsigned long long)__cvta_generic_to_shared(&s_tmem)),
+                         "n"(TM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
     __syncthreads();
+    int tmc = 0;  // block columns of this warp's slice of the CTA's first group that live in tensor memory
+    unsigned tm = 0;
+    if (TMEM) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tm = s_tmem + ((unsigned)((warp & 3) * 32) << 16) + (warp >= 4 ? TM_COLS / 2 : 0);
+        const long long sl0 = (long long)blockIdx.x * FS_SLICES + warp;
+        if (sl0 < a.n_slices && !sh.done[0]) {
+            const int q0 = a.slice_ptr[sl0];
+            tmc = min((a.slice_ptr[sl0 + 1] - q0) >> 5, FS_TM_BLOCKS);
+            const double *v = a.val + (long long)(q0 >> 5) * 288 + lane;
+            for (int t = 0; t < tmc; t++) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) tmem_st_double(tm + t * 18 + 2 * q, v[288 * t + 32 * q]);
+            }
+        }
+        tmem_wait_st();
+    }
 
     // generation "-1": r_0 = b, p = 0, Ap = 0; x = 0
     for (int s = 0; s < a.n_sys; s++) {
@@ -1258,14 +1295,21 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
         acc = warp_sum(acc);
         if (lane == 0) sh.warp[0][s][warp] = acc;
     }
-    fused_allreduce<1, 10>(a, grid, sh, epoch, [&](int ss, double t0, double, double) {
-        sh.normb[ss] = t0;
-        sh.rho[ss] = t0;
-        sh.tot0[ss] = t0;
-        if (!sh.done[ss] && t0 == 0.0) sh.done[ss] = 1;
-    });
-
     unsigned light_target = 0;
+    {
+        auto first = [&](int ss, double t0, double, double) {
+            sh.normb[ss] = t0;
+            sh.rho[ss] = t0;
+            sh.tot0[ss] = t0;
+            if (!sh.done[ss] && t0 == 0.0) sh.done[ss] = 1;
+        };
+        if (TMEM) {  // plain launch: counter barrier instead of grid.sync
+            const double *part = fused_publish_sync<1, true>(a, grid, sh, epoch, &light_target);
+            fused_collect<1, 10>(a, sh, part, first);
+        } else {
+            fused_allreduce<1, 10>(a, grid, sh, epoch, first);
+        }
+    }
     unsigned xe = 0;
     FxPrev fx_prev;
     int cur = 0;
@@ -1322,7 +1366,23 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
                         const double4 ro = Ro[row], ao = Ao[row], po = Po[row];
                         double4 xv = X4[row];
                         double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-                        for (int j0 = 0; j0 < w; j0 += STR_BATCH) {
+                        int jfirst = 0;
+                        if (TMEM && g == (long long)blockIdx.x) {  // this group's first columns live in tensor memory
+                            for (int t = 0; t < tmc; t++) {
+                                unsigned mw[18];
+                                tmem_ld_x16(tm + t * 18, mw);
+                                tmem_ld_x2(tm + t * 18 + 16, mw + 16);
+                                const double *pj = hv + 3 * lc[32 * t];
+                                const double px = pj[0], py = pj[1], pz = pj[2];
+                                tmem_wait_ld();
+                                double md[9];
+#pragma unroll
+                                for (int q = 0; q < 9; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
+                                JF_BLOCK_FMA(md, 1, px, py, pz)
+                            }
+                            jfirst = tmc;
+                        }
+                        for (int j0 = jfirst; j0 < w; j0 += STR_BATCH) {
                             int c[STR_BATCH];
                             double m[STR_BATCH][9];
 #pragma unroll
@@ -1411,13 +1471,26 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
         acc = warp_sum(acc);
         if (lane == 0) sh.warp[0][s][warp] = acc;
     }
-    if (a.apply_update) fused_allreduce<1, 10>(a, grid, sh, epoch, [&](int ss, double t0, double, double) { sh.tot0[ss] = t0; });
+    if (a.apply_update) {
+        auto last = [&](int ss, double t0, double, double) { sh.tot0[ss] = t0; };
+        if (TMEM) {
+            const double *part = fused_publish_sync<1, true>(a, grid, sh, epoch, &light_target);
+            fused_collect<1, 10>(a, sh, part, last);
+        } else {
+            fused_allreduce<1, 10>(a, grid, sh, epoch, last);
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x < a.n_sys && a.state[threadIdx.x].active) {
         const int q = threadIdx.x;
         a.state[q].cg_iters = sh.iters[q];
         a.state[q].normb = sh.normb[q];
         a.state[q].resid = sh.rho[q];
         if (a.apply_update) a.state[q].du = a.step * a.step * sh.tot0[q];
+    }
+    if (TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TM_COLS) : "memory");
     }
 }
 
@@ -1580,11 +1653,13 @@ int jf_cg_pair_launch(jf_ctx *c, CgArgs &a) {
 // streaming counterpart: needs the group halo lists of the halo-staged streaming kernel (cg_stream_halo)
 int jf_cg_fused_stream_configure(jf_ctx *c) {
     c->cg_fused_stream = 0;
+    c->cg_fused_stream_tmem = 0;
     if (!c->cg_stream_halo || c->n_sys > F_MAX_SYS || getenv("JF_CG_CLASSIC")) return 0;
     const size_t smem = (size_t)c->cg_hmax * 3 * sizeof(double);
-    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_stream_kernel, FS_THREADS, smem));
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_stream_kernel<false>, FS_THREADS, smem));
     if (per_sm < 1) return 0;
     const long long n_groups = (c->n_slices + FS_SLICES - 1) / FS_SLICES;
     long long grid = std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(n_groups, c->sm_count));
@@ -1592,6 +1667,12 @@ int jf_cg_fused_stream_configure(jf_ctx *c) {
     c->cg_fused_stream_grid = (int)grid;
     c->cg_fused_smem = smem;
     c->cg_fused_stream = 1;
+    // tensor-memory cache of each CTA's first group (one system, default switches, two CTAs per SM for 256 columns each).
+    // The occupancy calculator answers 1 for kernels that allocate tensor memory (see jf_cg_pair_configure): the twin's
+    // answer above stands in, and the kernel is launched plainly.
+    const char *e = getenv("JF_CG_STREAM_TMEM");
+    if (c->n_sys == 1 && per_sm <= 2 && (e ? atoi(e) != 0 : FS_DEFAULT_TMEM != 0) && !getenv("JF_CG_CGSYNC") && !getenv("JF_CG_SLOT_SUMS"))
+        c->cg_fused_stream_tmem = 1;
     return 1;
 }
 
@@ -1623,8 +1704,12 @@ int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
     a.r1 = c->d_r1;
     a.Ap1 = c->d_Ap1;
     void *args[] = {&a};
-    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_fused_stream_kernel, dim3(c->cg_fused_stream_grid), dim3(FS_THREADS), args,
-                                        c->cg_fused_smem, c->stream));
+    if (c->cg_fused_stream_tmem && a.light_barrier && a.exact_sums)
+        JF_CUDA(cudaLaunchKernel((void *)jf_cg_fused_stream_kernel<true>, dim3(c->cg_fused_stream_grid), dim3(FS_THREADS), args, c->cg_fused_smem,
+                                 c->stream));
+    else
+        JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_fused_stream_kernel<false>, dim3(c->cg_fused_stream_grid), dim3(FS_THREADS), args,
+                                            c->cg_fused_smem, c->stream));
     return 0;
 }
 

@@ -130,12 +130,13 @@ class _Claimer:
             self.pos = 0
 
     def take(self, count):
-        """Up to ``count`` load-case indices, [] when the list is exhausted.  Near the end of a shared list the draws
-        shrink to single cases: a batch drawn by one rank while the others have nothing left would be the whole tail."""
+        """Up to ``count`` load-case indices, [] when the list is exhausted.  When fewer cases are left in a shared list than
+        there are ranks the draws shrink to single cases (measured on 8 GPUs: shrinking earlier, at 2 x ranks, costs 3 %:
+        two rounds of single solves instead of one round of pairs)."""
         if self.store is not None:
             if count > 1 and self.world > 1:
                 taken = int(self.store.add(self.key, 0))
-                if self.n - taken <= self.world * count:
+                if self.n - taken <= self.world:   # fewer cases left than ranks: one each (a pair costs 1.15 x a single solve)
                     count = 1
             end = int(self.store.add(self.key, count))
             start = end - count
