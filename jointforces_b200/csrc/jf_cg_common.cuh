@@ -39,6 +39,7 @@ struct CgArgs {
     const int32_t *halo_nodes;  // concatenated halo lists
     const uint16_t *lcol;       // (n_slots) block column as index into the owning CTA's halo list
     int hmax, ctas_per_sys;
+    int fs_sm_blocks = 0;        // jf_cg_fused_stream_kernel: block columns of a CTA's first group cached in shared memory
     int fmax = 0, tail_max = 0;  // jf_cg_pair_kernel: most foreign halo nodes / most shared-memory block columns of any CTA
     double tol;
     long long maxiter;

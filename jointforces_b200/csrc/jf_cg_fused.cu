@@ -1258,6 +1258,8 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
     }
     __syncthreads();
     int tmc = 0;  // block columns of this warp's slice of the CTA's first group that live in tensor memory
+    int smc = 0;  // ... and the next ones in shared memory behind the halo: [column][component][thread], conflict-free
+    double *msm = hv + (size_t)a.hmax * 3 + threadIdx.x;
     unsigned tm = 0;
     if (TMEM) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1273,6 +1275,18 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
             }
         }
         tmem_wait_st();
+    }
+    if (a.fs_sm_blocks > 0 && a.n_sys == 1) {
+        const long long sl0 = (long long)blockIdx.x * FS_SLICES + warp;
+        if (sl0 < a.n_slices && !sh.done[0]) {
+            const int q0 = a.slice_ptr[sl0];
+            smc = min(((a.slice_ptr[sl0 + 1] - q0) >> 5) - tmc, a.fs_sm_blocks);
+            const double *v = a.val + (long long)(q0 >> 5) * 288 + lane;
+            for (int t = 0; t < smc; t++) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) msm[(t * 9 + q) * FS_THREADS] = v[288 * (tmc + t) + 32 * q];
+            }
+        }
     }
 
     // generation "-1": r_0 = b, p = 0, Ap = 0; x = 0
@@ -1381,6 +1395,15 @@ __global__ void __launch_bounds__(FS_THREADS, 2) jf_cg_fused_stream_kernel(CgArg
                                 JF_BLOCK_FMA(md, 1, px, py, pz)
                             }
                             jfirst = tmc;
+                        }
+                        if (g == (long long)blockIdx.x) {  // the next columns of the group from shared memory
+                            for (int t = 0; t < smc; t++) {
+                                const double *pj = hv + 3 * lc[32 * (jfirst + t)];
+                                const double px = pj[0], py = pj[1], pz = pj[2];
+                                const double *mm = msm + t * 9 * FS_THREADS;
+                                JF_BLOCK_FMA(mm, FS_THREADS, px, py, pz)
+                            }
+                            jfirst += smc;
                         }
                         for (int j0 = jfirst; j0 < w; j0 += STR_BATCH) {
                             int c[STR_BATCH];
@@ -1655,11 +1678,23 @@ int jf_cg_fused_stream_configure(jf_ctx *c) {
     c->cg_fused_stream = 0;
     c->cg_fused_stream_tmem = 0;
     if (!c->cg_stream_halo || c->n_sys > F_MAX_SYS || getenv("JF_CG_CLASSIC")) return 0;
-    const size_t smem = (size_t)c->cg_hmax * 3 * sizeof(double);
+    size_t smem = (size_t)c->cg_hmax * 3 * sizeof(double);
+    // one system: the shared memory two CTAs per SM leave free holds further block columns of each CTA's first group
+    c->cg_fs_sm_blocks = 0;
+    if (c->n_sys == 1 && !getenv("JF_CG_STREAM_NO_SMEM_CACHE")) {
+        const size_t per_block = (size_t)9 * FS_THREADS * sizeof(double), budget = 106 * 1024;
+        if (smem + per_block <= budget) c->cg_fs_sm_blocks = (int)std::min<size_t>(8, (budget - smem) / per_block);
+        smem += c->cg_fs_sm_blocks * per_block;
+    }
     JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     JF_CUDA(cudaFuncSetAttribute(jf_cg_fused_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_stream_kernel<false>, FS_THREADS, smem));
+    if (per_sm < 2 && c->cg_fs_sm_blocks) {  // never trade the second CTA per SM for the cache
+        smem -= c->cg_fs_sm_blocks * (size_t)9 * FS_THREADS * sizeof(double);
+        c->cg_fs_sm_blocks = 0;
+        JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_fused_stream_kernel<false>, FS_THREADS, smem));
+    }
     if (per_sm < 1) return 0;
     const long long n_groups = (c->n_slices + FS_SLICES - 1) / FS_SLICES;
     long long grid = std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(n_groups, c->sm_count));
@@ -1704,6 +1739,7 @@ int jf_cg_fused_stream_launch(jf_ctx *c, CgArgs &a) {
     a.r1 = c->d_r1;
     a.Ap1 = c->d_Ap1;
     void *args[] = {&a};
+    a.fs_sm_blocks = c->cg_fs_sm_blocks;
     if (c->cg_fused_stream_tmem && a.light_barrier && a.exact_sums)
         JF_CUDA(cudaLaunchKernel((void *)jf_cg_fused_stream_kernel<true>, dim3(c->cg_fused_stream_grid), dim3(FS_THREADS), args, c->cg_fused_smem,
                                  c->stream));
