@@ -228,6 +228,36 @@ __device__ __forceinline__ void cg_write_state(const CgArgs &a, CgShared &sh) {
     }
 }
 
+// ---- tensor memory as plain storage (jf_cg_pair_kernel, jf_cg_fused_stream_kernel, jf_cg_stream_kernel) -----------------------------------------------------
+// TMEM (256 KB per SM, 128 lanes x 512 columns of 32 bits) is idle in a kernel without tensor-core work.  A CTA of four
+// warps owns one lane per thread (warp w may touch lanes 32 (w % 4) ... + 31), so with 256 allocated columns every thread
+// has 1 KB = 128 doubles of private storage that is read by tcgen05.ld straight into registers -- not through the
+// LSU / shared-memory pipe the block rows' p gathers need.  The shared-memory tail of a row lives there instead.
+__device__ __forceinline__ void tmem_st_double(unsigned taddr, double v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+#define TM_R4(r, o) "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3])
+__device__ __forceinline__ void tmem_ld_x2(unsigned taddr, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(unsigned taddr, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : TM_R4(r, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(unsigned taddr, unsigned *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TM_R4(r, 0), TM_R4(r, 4), TM_R4(r, 8), TM_R4(r, 12)
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(unsigned taddr, unsigned *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : TM_R4(r, 0), TM_R4(r, 4), TM_R4(r, 8), TM_R4(r, 12), TM_R4(r, 16), TM_R4(r, 20), TM_R4(r, 24), TM_R4(r, 28)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 #define JF_BLOCK_FMA(vj, STRIDE, px, py, pz)  \
     y0 = fma((vj)[0 * (STRIDE)], px, y0);     \
     y0 = fma((vj)[1 * (STRIDE)], py, y0);     \

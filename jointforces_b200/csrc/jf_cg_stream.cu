@@ -12,16 +12,59 @@ namespace {
 // =================================================================================================
 // streaming: matrix from L2/HBM, vectors in global memory, warps loop over (system, slice) items
 // =================================================================================================
+// CACHE (one system): the kernel is persistent and warp `wg` always starts with slice `wg`; the first ST_TM_BLOCKS block
+// columns of that slice live in the thread's share of TENSOR MEMORY (one CTA per SM: all 512 columns, the four warps of
+// a lane quarter take 128 each = 7 blocks per thread) and the next `fs_sm_blocks` in shared memory for the whole CG solve:
+// on an HBM-bound matrix that is 148 SMs x (229 KB + 184 KB) = 61 MB that no longer come from DRAM in every iteration
+// (BASELINE configs[4]: 9.5 % of 643 MB).  Same summation order, same bits.
+constexpr int ST_TM_COLS = 512;
+constexpr int ST_TM_BLOCKS = (ST_TM_COLS / 4) / 18;
+
+template <bool CACHE>
 __global__ void __launch_bounds__(JF_CG_BLOCK, 1) jf_cg_stream_kernel(CgArgs a) {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ double st_cache[];  // CACHE: fs_sm_blocks x 9 x JF_CG_BLOCK doubles, [column][component][thread]
     __shared__ CgShared sh;
+    __shared__ unsigned s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const long long wg = (long long)warp * gridDim.x + blockIdx.x;
     const long long nwg = (long long)gridDim.x * nwarps;
     const long long vstride = a.Nf_pad * 4;
     unsigned epoch = 0;
 
+    if (CACHE) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"l"((unsigned long long)__cvta_generic_to_shared(&s_tmem)),
+                         "n"(ST_TM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
     cg_init_flags(a, sh);
+    int tmc = 0, smc = 0;  // block columns of slice `wg` in tensor memory / in shared memory
+    unsigned tm = 0;
+    const double *msm = st_cache + threadIdx.x;
+    if (CACHE) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tm = s_tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(warp >> 2) * (ST_TM_COLS / 4);
+        if (wg < a.n_slices && !sh.done[0]) {
+            const int q0 = a.slice_ptr[wg];
+            const int w0 = (a.slice_ptr[wg + 1] - q0) >> 5;
+            tmc = min(w0, ST_TM_BLOCKS);
+            smc = min(w0 - tmc, a.fs_sm_blocks);
+            const double *v = a.val + (long long)(q0 >> 5) * 288 + lane;
+            for (int t = 0; t < tmc; t++) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) tmem_st_double(tm + t * 18 + 2 * q, v[288 * t + 32 * q]);
+            }
+            for (int t = 0; t < smc; t++) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) st_cache[(t * 9 + q) * JF_CG_BLOCK + threadIdx.x] = v[288 * (tmc + t) + 32 * q];
+            }
+        }
+        tmem_wait_st();
+    }
 
     // ---- init: x = 0, r = b, pold = 0, normb = b.b --------------------------------------------
     for (int s = 0; s < a.n_sys; s++) {
@@ -68,7 +111,29 @@ __global__ void __launch_bounds__(JF_CG_BLOCK, 1) jf_cg_stream_kernel(CgArgs a) 
                     const int32_t *ci = a.sell_col + q0 + lane;
                     const double4 ri = r4[row], pi = po4[row];
                     double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-                    for (int j0 = 0; j0 < w; j0 += STR_BATCH) {
+                    int jfirst = 0;
+                    if (CACHE && sl == wg) {  // the cached columns of the warp's first slice: one at a time, same order
+                        for (int t = 0; t < tmc + smc; t++) {
+                            const int cc = ci[32 * t];
+                            const double4 rv = ld_node(r4 + cc), pv = ld_node(po4 + cc);
+                            double md[9];
+                            if (t < tmc) {
+                                unsigned mw[18];
+                                tmem_ld_x16(tm + t * 18, mw);
+                                tmem_ld_x2(tm + t * 18 + 16, mw + 16);
+                                tmem_wait_ld();
+#pragma unroll
+                                for (int q = 0; q < 9; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 9; q++) md[q] = msm[((t - tmc) * 9 + q) * JF_CG_BLOCK];
+                            }
+                            const double px = fma(beta, pv.x, rv.x), py = fma(beta, pv.y, rv.y), pz = fma(beta, pv.z, rv.z);
+                            JF_BLOCK_FMA(md, 1, px, py, pz)
+                        }
+                        jfirst = tmc + smc;
+                    }
+                    for (int j0 = jfirst; j0 < w; j0 += STR_BATCH) {
                         int c[STR_BATCH];
                         double4 rj[STR_BATCH], pj[STR_BATCH];
                         double m[STR_BATCH][9];
@@ -157,6 +222,11 @@ __global__ void __launch_bounds__(JF_CG_BLOCK, 1) jf_cg_stream_kernel(CgArgs a) 
         grid_allreduce(a, grid, sh.warp, sh.tot, epoch);
     }
     cg_write_state(a, sh);
+    if (CACHE) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(ST_TM_COLS) : "memory");
+    }
 }
 constexpr int SH_SLICES = 8;               // slices per halo group = warps per CTA
 constexpr int SH_THREADS = SH_SLICES * 32;
@@ -406,10 +476,37 @@ int jf_cg_stream_configure(jf_ctx *c) {
         }
     }
     int per_sm = 0;
-    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_stream_kernel, JF_CG_BLOCK, 0));
+    JF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jf_cg_stream_kernel<false>, JF_CG_BLOCK, 0));
     if (per_sm < 1) {
         jf_set_error("CG kernel does not fit on an SM");
         return JF_ERR_CUDA;
+    }
+    // one system on one CTA per SM: cache the first columns of every warp's first slice in tensor + shared memory
+    // (one CTA per SM is also what the occupancy calculator grants a kernel that allocates tensor memory, so the
+    //  cooperative launch stays)
+    c->cg_stream_cache = 0;
+    c->cg_stream_smem = 0;
+    // MEASURED SLOWER on the HBM-bound 503 k-node mesh (168.8 vs 122.0 us per iteration, profiles/README.md r3n): while every
+    // warp works through its cached slice nothing streams from DRAM, and the 184 KB of shared memory leave the vector
+    // gathers 50 KB of L1.  Opt-in: JF_CG_STREAM_CACHE=1.
+    if (c->n_sys == 1 && per_sm == 1 && getenv("JF_CG_STREAM_CACHE")) {
+        cudaFuncAttributes fa;
+        int max_optin = 0;
+        if (cudaFuncGetAttributes(&fa, jf_cg_stream_kernel<true>) == cudaSuccess &&
+            cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) == cudaSuccess) {
+            const size_t per_block = (size_t)9 * JF_CG_BLOCK * sizeof(double);
+            const long long avail = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024;
+            const int blocks = avail > 0 ? (int)std::min<long long>(8, avail / (long long)per_block) : 0;
+            const size_t smem = blocks * per_block;
+            int p2 = 0;
+            if (cudaFuncSetAttribute(jf_cg_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, jf_cg_stream_kernel<true>, JF_CG_BLOCK, smem) == cudaSuccess && p2 >= 1) {
+                c->cg_stream_cache = 1;
+                c->cg_stream_smem = smem;
+                c->cg_fs_sm_blocks = blocks;
+            }
+        }
+        cudaGetLastError();
     }
     // enough CTAs to give every slice of every system its own warp, at most what can be co-resident
     const long long items = (long long)c->n_sys * c->n_slices;
@@ -434,6 +531,12 @@ int jf_cg_stream_launch(jf_ctx *c, CgArgs &a) {
                                             c->stream));
         return 0;
     }
-    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_stream_kernel, dim3(c->cg_grid), dim3(JF_CG_BLOCK), args, 0, c->stream));
+    if (c->cg_stream_cache && c->cg_grid <= c->sm_count) {
+        a.fs_sm_blocks = (int)(c->cg_stream_smem / ((size_t)9 * JF_CG_BLOCK * sizeof(double)));
+        JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_stream_kernel<true>, dim3(c->cg_grid), dim3(JF_CG_BLOCK), args, c->cg_stream_smem,
+                                            c->stream));
+        return 0;
+    }
+    JF_CUDA(cudaLaunchCooperativeKernel((void *)jf_cg_stream_kernel<false>, dim3(c->cg_grid), dim3(JF_CG_BLOCK), args, 0, c->stream));
     return 0;
 }

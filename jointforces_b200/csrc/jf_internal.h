@@ -135,7 +135,8 @@ struct jf_ctx {
     int64_t Nf_pad = 0;
     double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_p0 = nullptr, *d_p1 = nullptr, *d_Ap = nullptr;
     double *d_r1 = nullptr, *d_Ap1 = nullptr;  // second generation for the single-reduction CG kernel
-    int cg_fused = 0, cg_fused_stream = 0, cg_fused_stream_grid = 0, cg_fused_stream_tmem = 0, cg_fs_sm_blocks = 0;
+    int cg_fused = 0, cg_fused_stream = 0, cg_fused_stream_grid = 0, cg_fused_stream_tmem = 0, cg_fs_sm_blocks = 0, cg_stream_cache = 0;
+    size_t cg_stream_smem = 0;
     unsigned cg_launch_seq = 0;  // CG launches so far (epoch tag of the Ap rows, jf_cg_fused.cu)
     size_t cg_fused_smem = 0;
     double *d_partial = nullptr;       // (2, S, cg_grid) block partial sums
