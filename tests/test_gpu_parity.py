@@ -551,3 +551,38 @@ def test_single_reduction_kernel_orderings_agree_bitwise(beams, monkeypatch):
         assert np.array_equal(o[2], ref[2]), label
         assert np.array_equal(o[1], ref[1]), label
         assert np.array_equal(o[0], ref[0]), label
+
+
+def test_on_chip_caches_of_the_streaming_kernels_are_transparent(beams, monkeypatch):
+    """The streaming single-reduction kernel keeps the first block columns of each CTA's first group of slices in tensor
+    memory and in shared memory (jf_cg_fused_stream_kernel<true>); the plain streaming kernel has the same cache as an
+    option.  A cached block is the same number read from another place and the summation order is unchanged, so every
+    switch setting gives identical bits."""
+    from jointforces_b200 import _lib
+    c = make_case(0.2, 300.0)
+    switches = ("JF_CG_STREAM_TMEM", "JF_CG_STREAM_NO_SMEM_CACHE", "JF_CG_CLASSIC", "JF_CG_NO_STREAM_HALO", "JF_CG_STREAM_CACHE")
+
+    def run(env, expect_fused):
+        for k in switches:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with _lib.Context(c["coords"], c["tets"], c["movable"], beams=beams, flags=_lib.JF_FLAG_NO_RESIDENT) as ctx:
+            assert (ctx.info()["cg_resident"], ctx.info()["cg_fused"]) == (0, expect_fused), ctx.info()
+            ctx.set_material(*COLLAGEN12)
+            ctx.set_targets(c["f_target"])
+            ctx.set_displacements(np.zeros_like(c["coords"]))
+            relrec, cgit, n = ctx.relax(0.0033, 12, 0.01)
+            return ctx.displacements(), relrec[0], cgit[0]
+
+    ref = run({}, 2)                                                   # tensor memory + shared memory (default)
+    for env in ({"JF_CG_STREAM_TMEM": "0"}, {"JF_CG_STREAM_NO_SMEM_CACHE": "1"},
+                {"JF_CG_STREAM_TMEM": "0", "JF_CG_STREAM_NO_SMEM_CACHE": "1"}):
+        out = run(env, 2)
+        assert np.array_equal(out[2], ref[2]) and np.array_equal(out[1], ref[1]) and np.array_equal(out[0], ref[0]), env
+    plain = {"JF_CG_CLASSIC": "1", "JF_CG_NO_STREAM_HALO": "1"}        # the plain two-reduction streaming kernel
+    ref = run(plain, 0)
+    out = run(dict(plain, JF_CG_STREAM_CACHE="1"), 0)
+    assert np.array_equal(out[2], ref[2]) and np.array_equal(out[1], ref[1]) and np.array_equal(out[0], ref[0])
+    for k in switches:
+        monkeypatch.delenv(k, raising=False)
