@@ -12,11 +12,12 @@ namespace {
 // =================================================================================================
 // streaming: matrix from L2/HBM, vectors in global memory, warps loop over (system, slice) items
 // =================================================================================================
-// CACHE (one system): the kernel is persistent and warp `wg` always starts with slice `wg`; the first ST_TM_BLOCKS block
-// columns of that slice live in the thread's share of TENSOR MEMORY (one CTA per SM: all 512 columns, the four warps of
+// CACHE (one system): the kernel is persistent and warp `wg` always works on slices wg, wg + nwg, ...; the first ST_TM_BLOCKS
+// block columns of ONE of them live in the thread's share of TENSOR MEMORY (one CTA per SM: all 512 columns, the four warps of
 // a lane quarter take 128 each = 7 blocks per thread) and the next `fs_sm_blocks` in shared memory for the whole CG solve:
-// on an HBM-bound matrix that is 148 SMs x (229 KB + 184 KB) = 61 MB that no longer come from DRAM in every iteration
-// (BASELINE configs[4]: 9.5 % of 643 MB).  Same summation order, same bits.
+// on an HBM-bound matrix that is 148 SMs x (229 KB + 110 KB) = 50 MB that no longer come from DRAM in every iteration
+// (BASELINE configs[4]: 8 % of 643 MB).  Which slice of a warp is cached rotates with the warp, so that at any moment most
+// warps stream.  Same summation order, same bits.
 constexpr int ST_TM_COLS = 512;
 constexpr int ST_TM_BLOCKS = (ST_TM_COLS / 4) / 18;
 
@@ -42,15 +43,20 @@ __global__ void __launch_bounds__(JF_CG_BLOCK, 1) jf_cg_stream_kernel(CgArgs a) 
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     cg_init_flags(a, sh);
-    int tmc = 0, smc = 0;  // block columns of slice `wg` in tensor memory / in shared memory
+    int tmc = 0, smc = 0;  // block columns of the cached slice in tensor memory / in shared memory
+    long long csl = -1;    // the cached slice of this warp
     unsigned tm = 0;
     const double *msm = st_cache + threadIdx.x;
     if (CACHE) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tm = s_tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(warp >> 2) * (ST_TM_COLS / 4);
-        if (wg < a.n_slices && !sh.done[0]) {
-            const int q0 = a.slice_ptr[wg];
-            const int w0 = (a.slice_ptr[wg + 1] - q0) >> 5;
+        // which of the warp's slices is cached rotates with the warp: at any moment only 1/K of the warps work on a cached
+        // slice, the others keep DRAM busy
+        const long long K = wg < a.n_slices ? (a.n_slices - wg + nwg - 1) / nwg : 0;
+        csl = K > 0 ? wg + ((long long)(warp + blockIdx.x) % K) * nwg : -1;
+        if (csl >= 0 && !sh.done[0]) {
+            const int q0 = a.slice_ptr[csl];
+            const int w0 = (a.slice_ptr[csl + 1] - q0) >> 5;
             tmc = min(w0, ST_TM_BLOCKS);
             smc = min(w0 - tmc, a.fs_sm_blocks);
             const double *v = a.val + (long long)(q0 >> 5) * 288 + lane;
@@ -112,24 +118,35 @@ __global__ void __launch_bounds__(JF_CG_BLOCK, 1) jf_cg_stream_kernel(CgArgs a) 
                     const double4 ri = r4[row], pi = po4[row];
                     double y0 = 0.0, y1 = 0.0, y2 = 0.0;
                     int jfirst = 0;
-                    if (CACHE && sl == wg) {  // the cached columns of the warp's first slice: one at a time, same order
-                        for (int t = 0; t < tmc + smc; t++) {
-                            const int cc = ci[32 * t];
-                            const double4 rv = ld_node(r4 + cc), pv = ld_node(po4 + cc);
-                            double md[9];
-                            if (t < tmc) {
-                                unsigned mw[18];
-                                tmem_ld_x16(tm + t * 18, mw);
-                                tmem_ld_x2(tm + t * 18 + 16, mw + 16);
-                                tmem_wait_ld();
+                    if (CACHE && sl == csl) {  // the cached columns of this slice: gathers in batches, blocks one at a time, same order
+                        for (int t0 = 0; t0 < tmc + smc; t0 += STR_BATCH) {
+                            double4 rv[STR_BATCH], pv[STR_BATCH];
 #pragma unroll
-                                for (int q = 0; q < 9; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 9; q++) md[q] = msm[((t - tmc) * 9 + q) * JF_CG_BLOCK];
+                            for (int k = 0; k < STR_BATCH; k++) {
+                                const int cc = (t0 + k < tmc + smc) ? ci[32 * (t0 + k)] : (int)row;
+                                rv[k] = ld_node(r4 + cc);
+                                pv[k] = ld_node(po4 + cc);
                             }
-                            const double px = fma(beta, pv.x, rv.x), py = fma(beta, pv.y, rv.y), pz = fma(beta, pv.z, rv.z);
-                            JF_BLOCK_FMA(md, 1, px, py, pz)
+#pragma unroll
+                            for (int k = 0; k < STR_BATCH; k++) {
+                                const int t = t0 + k;
+                                if (t < tmc + smc) {
+                                    double md[9];
+                                    if (t < tmc) {
+                                        unsigned mw[18];
+                                        tmem_ld_x16(tm + t * 18, mw);
+                                        tmem_ld_x2(tm + t * 18 + 16, mw + 16);
+                                        tmem_wait_ld();
+#pragma unroll
+                                        for (int q = 0; q < 9; q++) md[q] = __hiloint2double((int)mw[2 * q + 1], (int)mw[2 * q]);
+                                    } else {
+#pragma unroll
+                                        for (int q = 0; q < 9; q++) md[q] = msm[((t - tmc) * 9 + q) * JF_CG_BLOCK];
+                                    }
+                                    const double px = fma(beta, pv[k].x, rv[k].x), py = fma(beta, pv[k].y, rv[k].y), pz = fma(beta, pv[k].z, rv[k].z);
+                                    JF_BLOCK_FMA(md, 1, px, py, pz)
+                                }
+                            }
                         }
                         jfirst = tmc + smc;
                     }
@@ -486,17 +503,21 @@ int jf_cg_stream_configure(jf_ctx *c) {
     //  cooperative launch stays)
     c->cg_stream_cache = 0;
     c->cg_stream_smem = 0;
-    // MEASURED SLOWER on the HBM-bound 503 k-node mesh (168.8 vs 122.0 us per iteration, profiles/README.md r3n): while every
-    // warp works through its cached slice nothing streams from DRAM, and the 184 KB of shared memory leave the vector
-    // gathers 50 KB of L1.  Opt-in: JF_CG_STREAM_CACHE=1.
-    if (c->n_sys == 1 && per_sm == 1 && getenv("JF_CG_STREAM_CACHE")) {
+    // Measured on the HBM-bound 503 k-node mesh (profiles/README.md r3n, r3r, r3s), us per iteration: no cache 122.0;
+    // first version (every warp's FIRST slice, one column at a time, 5 columns in shared memory) 168.8 -- nothing streams
+    // while all warps sit on their cached slices, and 184 KB of shared memory leave the vector gathers 50 KB of L1;
+    // rotated cached slice + batched gathers, tensor memory only 119.2; plus 1 / 2 / 3 / 4 / 5 columns in shared
+    // memory 118.7 / 118.0 / 117.6 / 121.0 / 169.2.  Default: tensor memory + 3 columns.  JF_CG_STREAM_NO_CACHE=1: off.
+    if (c->n_sys == 1 && per_sm == 1 && !getenv("JF_CG_STREAM_NO_CACHE")) {
         cudaFuncAttributes fa;
         int max_optin = 0;
         if (cudaFuncGetAttributes(&fa, jf_cg_stream_kernel<true>) == cudaSuccess &&
             cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) == cudaSuccess) {
             const size_t per_block = (size_t)9 * JF_CG_BLOCK * sizeof(double);
             const long long avail = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024;
-            const int blocks = avail > 0 ? (int)std::min<long long>(8, avail / (long long)per_block) : 0;
+            const char *eb = getenv("JF_CG_STREAM_CACHE_SMEM");   // block columns in shared memory on top of tensor memory (default
+            const int want = eb ? atoi(eb) : 3;                   //  three: beyond that the vector gathers lose their L1)
+            const int blocks = avail > 0 ? (int)std::min<long long>(std::max(0, std::min(want, 8)), avail / (long long)per_block) : 0;
             const size_t smem = blocks * per_block;
             int p2 = 0;
             if (cudaFuncSetAttribute(jf_cg_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&

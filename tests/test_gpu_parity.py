@@ -555,12 +555,11 @@ def test_single_reduction_kernel_orderings_agree_bitwise(beams, monkeypatch):
 
 def test_on_chip_caches_of_the_streaming_kernels_are_transparent(beams, monkeypatch):
     """The streaming single-reduction kernel keeps the first block columns of each CTA's first group of slices in tensor
-    memory and in shared memory (jf_cg_fused_stream_kernel<true>); the plain streaming kernel has the same cache as an
-    option.  A cached block is the same number read from another place and the summation order is unchanged, so every
+    memory and in shared memory (jf_cg_fused_stream_kernel<true>); the plain streaming kernel caches the first columns of one slice per warp.  A cached block is the same number read from another place and the summation order is unchanged, so every
     switch setting gives identical bits."""
     from jointforces_b200 import _lib
     c = make_case(0.2, 300.0)
-    switches = ("JF_CG_STREAM_TMEM", "JF_CG_STREAM_NO_SMEM_CACHE", "JF_CG_CLASSIC", "JF_CG_NO_STREAM_HALO", "JF_CG_STREAM_CACHE")
+    switches = ("JF_CG_STREAM_TMEM", "JF_CG_STREAM_NO_SMEM_CACHE", "JF_CG_CLASSIC", "JF_CG_NO_STREAM_HALO", "JF_CG_STREAM_NO_CACHE")
 
     def run(env, expect_fused):
         for k in switches:
@@ -582,7 +581,7 @@ def test_on_chip_caches_of_the_streaming_kernels_are_transparent(beams, monkeypa
         assert np.array_equal(out[2], ref[2]) and np.array_equal(out[1], ref[1]) and np.array_equal(out[0], ref[0]), env
     plain = {"JF_CG_CLASSIC": "1", "JF_CG_NO_STREAM_HALO": "1"}        # the plain two-reduction streaming kernel
     ref = run(plain, 0)
-    out = run(dict(plain, JF_CG_STREAM_CACHE="1"), 0)
+    out = run(dict(plain, JF_CG_STREAM_NO_CACHE="1"), 0)
     assert np.array_equal(out[2], ref[2]) and np.array_equal(out[1], ref[1]) and np.array_equal(out[0], ref[0])
     for k in switches:
         monkeypatch.delenv(k, raising=False)
