@@ -17,4 +17,4 @@ st, info = ctx.stats(), ctx.info()
 by = cg_bytes_per_iteration(info)
 print(wl, info)
 print("cg iters", it.tolist(), "ms_cg %.3f  us/iter %.2f  algorithmic GB/s %.1f  bytes/iter %.4g" % (
-    st["ms_cg"], st["ms_cg"] * 1e3 / it[0], by * it[0] / (st["ms_cg"] * 1e-3) / 1e9, by))
+    st["ms_cg"], st["ms_cg"] * 1e3 / it[0], float(by) * float(it[0]) / (st["ms_cg"] * 1e-3) / 1e9, by))
