@@ -149,7 +149,7 @@ struct jf_ctx {
     int elem_variant = 0;  // JF_ELEM_VARIANT: unroll / occupancy experiments of the element kernel (4 lanes)
     int cg_wmax = 1, cg_resident = 0, cg_res_warps = 0, cg_hmax = 0, cg_ctas_per_sys = 0;
     int cg_foreign_max = 0;
-    // two systems side by side (jf_cg_pair_kernel, jf_cg_fused.cu)
+    // two systems side by side (jf_cg_pair_kernel, jf_cg_pair.cu)
     int cg_pair = 0, cg_pair_ctas = 0, cg_pair_hmax = 0, cg_pair_fmax = 0, cg_pair_tail = 0;
     size_t cg_pair_smem = 0;
     int32_t *d_pair_halo_ptr = nullptr, *d_pair_halo_nodes = nullptr;

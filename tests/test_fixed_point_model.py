@@ -1,4 +1,4 @@
-"""CPU model of the fixed-point all-reduce of the single-reduction CG kernels (csrc/jf_cg_fused.cu:fused_fx_allreduce):
+"""CPU model of the fixed-point all-reduce of the single-reduction CG kernels (csrc/jf_cg_allreduce.cuh:fused_fx_allreduce):
 the constants are read from the source, the encode / accumulate / decode steps are restated with Python integers and
 checked for the invariants the kernel relies on -- limbs never spill into the arrival count, the count is exact for
 every grid size up to 1023, the decoded total is the exact sum of the partials up to one rounding (plus the bits
@@ -11,7 +11,7 @@ from fractions import Fraction
 import numpy as np
 import pytest
 
-SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jointforces_b200", "csrc", "jf_cg_fused.cu")
+SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jointforces_b200", "csrc", "jf_cg_allreduce.cuh")
 
 
 def constants():
