@@ -230,3 +230,25 @@ def test_killed_solve_leaves_its_relaxation_record(tmp_path):
     assert proc.returncode == -signal.SIGKILL
     rows = np.atleast_2d(np.loadtxt(name))
     assert 2 <= len(rows) < 78 and rows.shape[1] == 3 and rows[0, 0] == 0 and np.all(rows[1:, 1] > 0)
+
+
+def test_sweep_in_pairs_equals_sweep_one_case_at_a_time(tmp_path):
+    """On the configs[2] mesh run_sweep relaxes two neighbouring pressures side by side (jf_cg_pair_kernel, the odd case
+    alone).  Same Newton counts and, within the BASELINE curve tolerance (in fact at the 1e-5 trajectory-noise level),
+    the same table rows and displacement fields as the sweep that relaxes one case at a time; folders complete."""
+    from jointforces_b200 import sweep
+    path = str(tmp_path / "cfg2.msh")
+    jf.mesh.spherical_inclusion(path, 100, 10000, 0.05)
+    values = np.array([0.3, 30.0, 40.0, 900.0, 1000.0])
+    t2 = sweep.run_sweep(path, str(tmp_path / "pairs"), values, jf.materials.collagen12)
+    t1 = sweep.run_sweep(path, str(tmp_path / "single"), values, jf.materials.collagen12, batch=1)
+    assert np.array_equal(t2['index'], np.arange(5)) and np.allclose(t2['pressure'], values)
+    ok = ~np.isnan(t1['y'])
+    assert np.array_equal(np.isnan(t2['y']), ~ok)
+    assert np.max(np.abs(t2['y'][ok] / t1['y'][ok] - 1)) < 1e-3
+    for i in range(5):
+        a, b = (np.loadtxt(str(tmp_path / d / ("simulation%06d" % i) / "relrec.txt")) for d in ("pairs", "single"))
+        assert a.shape == b.shape                                           # same number of Newton steps
+        Ua, Ub = (jf.simulation.load_solver(str(tmp_path / d / ("simulation%06d" % i) / "solver.saenopy")).mesh.displacements
+                  for d in ("pairs", "single"))
+        assert np.linalg.norm(Ua - Ub) / np.linalg.norm(Ub) < 1e-4
